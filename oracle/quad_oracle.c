@@ -1,0 +1,302 @@
+/* quad_oracle.c -- CPU restatement of gym-rotor's env.step() hot path (see quad_oracle.h).
+ * TEST INFRASTRUCTURE ONLY.  Build: make -C oracle  (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+#include "quad_oracle.h"
+#include "dop853_tableau.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ---- tableau as dense arrays (zeros skipped at use) ------------------------------------------------ */
+#define TAB(T, name)                                                                                       \
+    static const T dopA##name[12][12] = {                                                                  \
+        {0},                                                                                               \
+        {(T)DOP_A1_0},                                                                                     \
+        {(T)DOP_A2_0, (T)DOP_A2_1},                                                                        \
+        {(T)DOP_A3_0, 0, (T)DOP_A3_2},                                                                     \
+        {(T)DOP_A4_0, 0, (T)DOP_A4_2, (T)DOP_A4_3},                                                        \
+        {(T)DOP_A5_0, 0, 0, (T)DOP_A5_3, (T)DOP_A5_4},                                                     \
+        {(T)DOP_A6_0, 0, 0, (T)DOP_A6_3, (T)DOP_A6_4, (T)DOP_A6_5},                                        \
+        {(T)DOP_A7_0, 0, 0, (T)DOP_A7_3, (T)DOP_A7_4, (T)DOP_A7_5, (T)DOP_A7_6},                           \
+        {(T)DOP_A8_0, 0, 0, (T)DOP_A8_3, (T)DOP_A8_4, (T)DOP_A8_5, (T)DOP_A8_6, (T)DOP_A8_7},              \
+        {(T)DOP_A9_0, 0, 0, (T)DOP_A9_3, (T)DOP_A9_4, (T)DOP_A9_5, (T)DOP_A9_6, (T)DOP_A9_7, (T)DOP_A9_8}, \
+        {(T)DOP_A10_0, 0, 0, (T)DOP_A10_3, (T)DOP_A10_4, (T)DOP_A10_5, (T)DOP_A10_6, (T)DOP_A10_7,         \
+         (T)DOP_A10_8, (T)DOP_A10_9},                                                                      \
+        {(T)DOP_A11_0, 0, 0, (T)DOP_A11_3, (T)DOP_A11_4, (T)DOP_A11_5, (T)DOP_A11_6, (T)DOP_A11_7,         \
+         (T)DOP_A11_8, (T)DOP_A11_9, (T)DOP_A11_10}};                                                      \
+    static const T dopB##name[12] = {(T)DOP_B0, 0, 0, 0, 0, (T)DOP_B5, (T)DOP_B6, (T)DOP_B7,               \
+                                     (T)DOP_B8, (T)DOP_B9, (T)DOP_B10, (T)DOP_B11};                        \
+    static const T dopE3##name[13] = {(T)DOP_E3_0, 0, 0, 0, 0, (T)DOP_E3_5, (T)DOP_E3_6, (T)DOP_E3_7,      \
+                                      (T)DOP_E3_8, (T)DOP_E3_9, (T)DOP_E3_10, (T)DOP_E3_11, 0};            \
+    static const T dopE5##name[13] = {(T)DOP_E5_0, 0, 0, 0, 0, (T)DOP_E5_5, (T)DOP_E5_6, (T)DOP_E5_7,      \
+                                      (T)DOP_E5_8, (T)DOP_E5_9, (T)DOP_E5_10, (T)DOP_E5_11, 0};
+TAB(double, _f64)
+TAB(float, _f32)
+
+/* ---- instantiate for double ------------------------------------------------------------------------ */
+#define REAL double
+#define RWD double
+#define SUF _f64
+#define FMA fma
+#define FABS fabs
+#define SQRT sqrt
+#define POW pow
+#define ATAN2 atan2
+#define COS cos
+#define SIN sin
+#define ACOS acos
+#define NEXTAFTER nextafter
+#define FMAX fmax
+#include "quad_oracle_impl.inc"
+#undef REAL
+#undef RWD
+#undef SUF
+#undef FMA
+#undef FABS
+#undef SQRT
+#undef POW
+#undef ATAN2
+#undef COS
+#undef SIN
+#undef ACOS
+#undef NEXTAFTER
+#undef FMAX
+
+/* ---- instantiate for float ------------------------------------------------------------------------- */
+#define REAL float
+#define RWD float
+#define SUF _f32
+#define FMA fmaf
+#define FABS fabsf
+#define SQRT sqrtf
+#define POW powf
+#define ATAN2 atan2f
+#define COS cosf
+#define SIN sinf
+#define ACOS acosf
+#define NEXTAFTER nextafterf
+#define FMAX fmaxf
+#include "quad_oracle_impl.inc"
+#undef REAL
+#undef RWD
+#undef SUF
+
+/* ---- public API ------------------------------------------------------------------------------------ */
+
+/* plain pthreads over contiguous env blocks (no OpenMP runtime: keeps the oracle free of libgomp clashes
+ * with the interpreter that loads it) */
+static int g_threads = 1;
+void qo_set_threads(int n) { g_threads = n > 0 ? n : 1; }
+int qo_get_max_threads(void)
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+typedef struct qo_job {
+    void (*fn)(void* ctx, int64_t lo, int64_t hi);
+    void* ctx;
+    int64_t lo, hi;
+} qo_job;
+
+static void* qo_job_main(void* a)
+{
+    qo_job* j = (qo_job*)a;
+    j->fn(j->ctx, j->lo, j->hi);
+    return 0;
+}
+
+static void qo_parallel_for(int64_t n, void (*fn)(void*, int64_t, int64_t), void* ctx)
+{
+    int nt = g_threads;
+    if (nt > 256) nt = 256;
+    if ((int64_t)nt > n) nt = (int)(n > 0 ? n : 1);
+    if (nt <= 1) { fn(ctx, 0, n); return; }
+    pthread_t th[256];
+    qo_job jobs[256];
+    int64_t chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        jobs[t].fn = fn; jobs[t].ctx = ctx;
+        jobs[t].lo = t * chunk; jobs[t].hi = (t + 1) * chunk < n ? (t + 1) * chunk : n;
+        if (jobs[t].lo > n) jobs[t].lo = n;
+        pthread_create(&th[t], 0, qo_job_main, &jobs[t]);
+    }
+    for (int t = 0; t < nt; ++t) pthread_join(th[t], 0);
+}
+
+int qo_obs_dim(int mode) { return mode == QO_MODE_COUPLED ? 23 : 18; }
+int qo_act_dim(int mode) { return mode == QO_MODE_DECOUPLED ? 5 : 4; }
+int qo_num_agents(int mode) { return mode == QO_MODE_DECOUPLED ? 2 : 1; }
+
+void qo_default_config(qo_config* c, int mode)
+{
+    memset(c, 0, sizeof(*c));
+    c->mode = mode;
+    c->integrator = QO_INT_DOP853;
+    c->act_f32 = 0;
+    c->dt = 1. / 200;          /* quad.py:60-61 */
+    c->g = 9.81;               /* quad.py:33 */
+    c->rtol = 1e-3;            /* scipy rk.py:86 */
+    c->atol = 1e-6;
+    c->x_lim = 1.0;            /* quad.py:104-106 */
+    c->v_lim = 4.0;
+    c->W_lim = 2 * M_PI;
+    c->eIx_lim = 3.0;          /* coupled:23-24 */
+    c->eIb1_lim = 3.0;
+    c->sat_sigma = 1.;         /* quad.py:91 */
+    c->alpha = 0.01;           /* args_parse.py:27 */
+    c->beta = 0.05;            /* args_parse.py:32 */
+    c->Cx = 6.0; c->CIx = 0.1; c->Cv = 0.4; c->Cw12 = 0.6;   /* args_parse.py:23-26 */
+    c->Cb1 = 6.0; c->CIb1 = 0.1; c->CW3 = 0.1;               /* args_parse.py:29-31 */
+    c->CW = c->Cw12;           /* quad.py:80 */
+    c->reward_min = -ceil(c->Cx + c->CIx + c->Cv + c->Cb1 + c->CIb1 + c->CW);  /* quad.py:81 */
+    c->reward_min_1 = -ceil(c->Cx + c->CIx + c->Cv + c->Cw12);                 /* quad.py:85 */
+    c->reward_min_2 = -ceil(c->Cb1 + c->CW3 + c->CIb1);                        /* quad.py:88 */
+    c->min_force = 0.5;        /* quad.py:39 */
+    c->euler_lim_deg = 85;     /* quad.py:107 */
+}
+
+typedef struct step_ctx {
+    const qo_config* c;
+    void *state, *integ; const void *params, *goal, *action; float* obs; void* reward; uint8_t* done;
+    int32_t* nfev; uint8_t* status;
+} step_ctx;
+
+static void step_range_f64(void* vp, int64_t lo, int64_t hi)
+{
+    step_ctx* s = (step_ctx*)vp;
+    const qo_config* c = s->c;
+    const int A = qo_act_dim(c->mode), O = qo_obs_dim(c->mode), G = qo_num_agents(c->mode);
+    for (int64_t e = lo; e < hi; ++e)
+        step_one_f64(c, (double*)s->state + 18 * e, (double*)s->integ + 8 * e, (const double*)s->params + 6 * e,
+                     (const double*)s->goal + 12 * e, (const double*)s->action + A * e, s->obs + O * e,
+                     (double*)s->reward + G * e, s->done + G * e, s->nfev ? s->nfev + e : 0,
+                     s->status ? s->status + e : 0);
+}
+
+static void step_range_f32(void* vp, int64_t lo, int64_t hi)
+{
+    step_ctx* s = (step_ctx*)vp;
+    const qo_config* c = s->c;
+    const int A = qo_act_dim(c->mode), O = qo_obs_dim(c->mode), G = qo_num_agents(c->mode);
+    for (int64_t e = lo; e < hi; ++e)
+        step_one_f32(c, (float*)s->state + 18 * e, (float*)s->integ + 8 * e, (const float*)s->params + 6 * e,
+                     (const float*)s->goal + 12 * e, (const float*)s->action + A * e, s->obs + O * e,
+                     (float*)s->reward + G * e, s->done + G * e, s->nfev ? s->nfev + e : 0,
+                     s->status ? s->status + e : 0);
+}
+
+int qo_step_f64(const qo_config* c, int64_t n, double* state, double* integ, const double* params,
+                const double* goal, const double* action, float* obs, double* reward, uint8_t* done,
+                int32_t* nfev, uint8_t* status)
+{
+    step_ctx s = {c, state, integ, params, goal, action, obs, reward, done, nfev, status};
+    qo_parallel_for(n, step_range_f64, &s);
+    return 0;
+}
+
+int qo_step_f32(const qo_config* c, int64_t n, float* state, float* integ, const float* params,
+                const float* goal, const float* action, float* obs, float* reward, uint8_t* done,
+                int32_t* nfev, uint8_t* status)
+{
+    step_ctx s = {c, state, integ, params, goal, action, obs, reward, done, nfev, status};
+    qo_parallel_for(n, step_range_f32, &s);
+    return 0;
+}
+
+int qo_norm_error_state_f64(const qo_config* c, int64_t n, const double* state, double* integ,
+                            const double* goal, float* obs)
+{
+    const int O = qo_obs_dim(c->mode);
+    for (int64_t e = 0; e < n; ++e) {
+        int bad = 0;
+        norm_error_state_f64(c, state + 18 * e, integ + 8 * e, goal + 12 * e, obs + O * e, &bad);
+    }
+    return 0;
+}
+
+int qo_rhs_f64(int64_t n, const double* y, const double* params, const double* fM, double* ydot)
+{
+    for (int64_t e = 0; e < n; ++e) {
+        rhs_par_f64 p;
+        p.m = params[6 * e]; p.J1 = params[6 * e + 2]; p.J3 = params[6 * e + 3]; p.g = 9.81;
+        p.f = fM[4 * e]; p.M[0] = fM[4 * e + 1]; p.M[1] = fM[4 * e + 2]; p.M[2] = fM[4 * e + 3];
+        p.n_svd = 0; p.svd_bad = 0;
+        rhs_f64(y + 18 * e, ydot + 18 * e, &p);
+    }
+    return 0;
+}
+
+int64_t qo_ensure_so3_f64(int64_t n, double* R)
+{
+    int64_t k = 0;
+    for (int64_t e = 0; e < n; ++e) k += ensure_so3_f64(R + 9 * e, 0);
+    return k;
+}
+
+/* ---- reset (quad.py:171-222, 338-404) with the uniforms supplied by the caller ------------------------ */
+
+static double lerp_u(double lo, double hi, double u) { return lo + (hi - lo) * u; }
+
+int qo_reset_from_uniforms_f64(const qo_config* c, int env_type, double udm_pct, int64_t n, const double* u,
+                               double* state, double* integ, double* params)
+{
+    (void)c;
+    const double m0 = 2.15, d0 = 0.23, J10 = 0.022, J30 = 0.035, ctf0 = 0.0135, ctw0 = 2.2; /* quad.py:28-32 */
+    for (int64_t e = 0; e < n; ++e) {
+        const double* q = u + 20 * e;
+        double* p = params + 6 * e;
+        p[0] = m0; p[1] = d0; p[2] = J10; p[3] = J30; p[4] = ctf0; p[5] = ctw0;
+        if (env_type == QO_ENV_TRAIN) { /* quad.py:368-386: U(nom -+ 10 %), c_tw -+ 5 % */
+            double r = udm_pct / 100.0;
+            p[0] = lerp_u(m0 - m0 * r, m0 + m0 * r, q[0]);
+            p[1] = lerp_u(d0 - d0 * r, d0 + d0 * r, q[1]);
+            p[2] = lerp_u(J10 - J10 * r, J10 + J10 * r, q[2]);
+            p[3] = lerp_u(J30 - J30 * r, J30 + J30 * r, q[3]);
+            p[4] = lerp_u(ctf0 - ctf0 * r, ctf0 + ctf0 * r, q[4]);
+            p[5] = lerp_u(ctw0 - ctw0 * (r / 2.), ctw0 + ctw0 * (r / 2.), q[5]);
+        }
+        double yaw = lerp_u(-M_PI, M_PI, q[6]); /* quad.py:339 */
+        double ix, iv, iR, iW;                  /* quad.py:340-356 */
+        if (env_type == QO_ENV_TRAIN) {
+            if (q[7] < 0.2) { ix = 0; iv = 0; iR = 0; iW = 0; }
+            else { ix = 0.6; iv = 4.0 * 0.5; iR = 50 * (M_PI / 180.); iW = 2 * M_PI * 0.5; }
+        } else { ix = 0.4; iv = 0; iR = 0; iW = 0; }
+        double* s = state + 18 * e;
+        for (int i = 0; i < 3; ++i) {
+            s[i] = lerp_u(-ix, ix, q[8 + i]);
+            s[3 + i] = lerp_u(-iv, iv, q[11 + i]);
+            s[15 + i] = lerp_u(-iW, iW, q[14 + i]);
+        }
+        double roll = lerp_u(-iR, iR, q[17]), pitch = lerp_u(-iR, iR, q[18]);
+        double cr = cos(roll), sr = sin(roll), cp = cos(pitch), sp = sin(pitch), cy = cos(yaw), sy = sin(yaw);
+        /* R = Rz(yaw) Ry(pitch) Rx(roll)  (scipy Rotation.from_euler('xyz'), quad.py:199), column-major */
+        s[6] = cy * cp;  s[9]  = cy * sp * sr - sy * cr;  s[12] = cy * sp * cr + sy * sr;
+        s[7] = sy * cp;  s[10] = sy * sp * sr + cy * cr;  s[13] = sy * sp * cr - cy * sr;
+        s[8] = -sp;      s[11] = cp * sr;                 s[14] = cp * cr;
+        for (int i = 0; i < 8; ++i) integ[8 * e + i] = 0.0;
+    }
+    return 0;
+}
+
+/* ---- Philox4x32-10 ----------------------------------------------------------------------------------- */
+
+void qo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
