@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference (/root/reference).
+
+TEST INFRASTRUCTURE.  Runs only in the build container (the reference tree does not travel to the GPU
+box); the produced .npz files are committed so that every test can run without the reference.
+
+    python oracle/make_golden.py            # all fixtures
+    python oracle/make_golden.py step kat1  # a subset
+
+Fixtures (float64 unless noted; every array is [T, ...] with one row per env.step() call):
+  step_{mono,modul}_{a64,a32}.npz  free-running episodes driven exactly like main.py:126-129,140-164,212-230
+        (reset -> trajgen.mark_traj_start/get_desired(mode 0) -> set_goal_state -> get_norm_error_state ->
+        loop) with U(-1,1) actions; per step: state_in, integ_in, params, goal, action, state_out,
+        integ_out, obs (f32), reward, done, nfev.  a32 = the action array is float32 (numpy then computes the
+        thrust in float32, coupled_yaw_wrapper.py:46-48).
+  kat1_modul_log.npz   the reference's own flight log results/MODUL_log_20250303_120200.dat (3600 x 40).
+  reset_samples.npz    reference reset('train') / reset('eval') draws (state + parameters), float32.
+  quad_v0.npz          base Quad-v0 env (T1..T4 actions), DOP853 and Euler integrators.
+  batch512.npz         512 envs x 100 steps, no resets: initial state/params, final state/integrals and the
+                       full reward/done history (SURVEY 8(d) config 2 at a size the reference finishes in ~2 min).
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrs)
+    print("wrote %s (%.0f KB)" % (path, os.path.getsize(path) / 1024))
+
+
+def gen_step(framework, act32, n_steps, seed):
+    env = rh.make_env(framework)
+    tg = rh.make_trajgen(env)
+    cnt = rh.RhsCounter(env)
+    rh.seed_all(seed)
+    A = 4 if framework == "MONO" else 5
+    rec = {k: [] for k in ("state_in", "integ_in", "params", "goal", "action", "state_out", "integ_out", "obs",
+                           "reward", "done", "nfev", "reset_state32", "episode_start")}
+    # main.py:126-129
+    state32 = env.reset(env_type='train', seed=seed)
+    xd, vd, b1d, b1d_dot, Wd = tg.get_desired(state32, 0)
+    env.set_goal_state(xd, vd, b1d, b1d_dot, Wd)
+    env.get_norm_error_state(framework)
+    new_episode = True
+    ep_steps = 0
+    for _ in range(n_steps):
+        ep_steps += 1
+        # main.py:145-147
+        st = env.get_current_state()
+        xd, vd, b1d, b1d_dot, Wd = tg.get_desired(st, 0)
+        env.set_goal_state(xd, vd, b1d, b1d_dot, Wd)
+        a = np.random.rand(A) * 2 - 1  # main.py:155
+        if act32:
+            a = a.astype(np.float32)
+        rec["state_in"].append(np.array(env.state, dtype=np.float64))
+        rec["integ_in"].append(rh.get_integ(env))
+        rec["params"].append(rh.get_params(env))
+        rec["goal"].append(rh.get_goal(env))
+        rec["action"].append(a.astype(np.float64))
+        rec["episode_start"].append(new_episode)
+        rec["reset_state32"].append(np.array(state32, dtype=np.float32))
+        new_episode = False
+        obs, rew, done, _, _ = env.step(a.copy())
+        rec["nfev"].append(cnt.take())
+        rec["state_out"].append(np.array(env.state, dtype=np.float64))
+        rec["integ_out"].append(rh.get_integ(env))
+        rec["obs"].append(np.concatenate(obs).astype(np.float32))
+        rec["reward"].append(np.array(rew, dtype=np.float64))
+        rec["done"].append(np.array(done, dtype=bool))
+        if any(done) or ep_steps == 400:  # main.py:212-230 (shorter time limit to see more resets)
+            state32 = env.reset(env_type='train', seed=seed)
+            tg.mark_traj_start(state32)
+            xd, vd, b1d, b1d_dot, Wd = tg.get_desired(state32, 0)
+            env.set_goal_state(xd, vd, b1d, b1d_dot, Wd)
+            env.get_norm_error_state(framework)
+            cnt.take()
+            new_episode = True
+            ep_steps = 0
+    return {k: np.array(v) for k, v in rec.items()}
+
+
+def make_step():
+    for fw, tag in (("MONO", "mono"), ("MODUL", "modul")):
+        _save("step_%s_a64.npz" % tag, **gen_step(fw, False, 1200, seed=11))
+        _save("step_%s_a32.npz" % tag, **gen_step(fw, True, 400, seed=12))
+
+
+def make_kat1():
+    rows = np.loadtxt(os.path.join(rh.REFERENCE_ROOT, "results", "MODUL_log_20250303_120200.dat"))
+    assert rows.shape == (3600, 40), rows.shape
+    _save("kat1_modul_log.npz", rows=rows)
+
+
+def make_reset():
+    out = {}
+    for fw in ("MONO",):
+        env = rh.make_env(fw)
+        rh.seed_all(2024)
+        for env_type, n in (("train", 8192), ("eval", 1024)):
+            st = np.empty((n, 18), np.float32); par = np.empty((n, 6), np.float32)
+            for i in range(n):
+                env.reset(env_type=env_type)
+                st[i] = env.state; par[i] = rh.get_params(env)
+            out["state_" + env_type] = st
+            out["params_" + env_type] = par
+    _save("reset_samples.npz", **out)
+
+
+def make_quad():
+    out = {}
+    for integ in ("solve_ivp", "euler"):
+        env = rh.make_base_env()
+        env.ode_integrator = integ
+        rh.seed_all(5)
+        env.reset(env_type='train')
+        rec = {k: [] for k in ("state_in", "params", "goal", "action", "state_out", "reward", "done")}
+        rng = np.random.default_rng(6)
+        for t in range(300):
+            goal = np.concatenate([rng.uniform(-.3, .3, 3), rng.uniform(-.3, .3, 3),
+                                   [np.cos(0.7), np.sin(0.7), 0.], np.zeros(3)])
+            rh.set_goal(env, goal)
+            a = rng.uniform(-1, 1, 4)
+            rec["state_in"].append(np.array(env.state, np.float64)); rec["params"].append(rh.get_params(env))
+            rec["goal"].append(goal); rec["action"].append(a)
+            obs, rew, done, _, _ = env.step(a.copy())
+            rec["state_out"].append(np.array(env.state, np.float64))
+            rec["reward"].append(np.array(rew, np.float64)); rec["done"].append(np.array(done, bool))
+            if done[0]:
+                env.reset(env_type='train')
+        for k, v in rec.items():
+            out["%s_%s" % (integ, k)] = np.array(v)
+    _save("quad_v0.npz", **out)
+
+
+def make_batch():
+    N, H = 512, 100
+    env = rh.make_env("MONO")
+    st0 = np.empty((N, 18)); par = np.empty((N, 6))
+    for s in range(N):
+        rh.seed_all(s)
+        env.reset(env_type='train')
+        st0[s] = env.state; par[s] = rh.get_params(env)
+    actions = np.random.default_rng(1).uniform(-1, 1, size=(H, N, 4))
+    goal = np.zeros(12); goal[6] = 1.0
+    stT = np.empty((N, 18)); igT = np.empty((N, 8))
+    reward = np.empty((H, N)); done = np.empty((H, N), bool); nfev = np.empty((H, N), np.int16)
+    obs_crc = np.empty(H, np.uint32)
+    obs_all = np.empty((H, N, 23), np.float32)
+    cnt = rh.RhsCounter(env)
+    for s in range(N):
+        rh.set_params(env, par[s]); env.state = st0[s].copy(); rh.set_integ(env, np.zeros(8)); rh.set_goal(env, goal)
+        cnt.take()
+        for t in range(H):
+            o, r, d, _, _ = env.step(actions[t, s].copy())
+            reward[t, s] = r[0]; done[t, s] = d[0]; nfev[t, s] = cnt.take(); obs_all[t, s] = o[0]
+        stT[s] = env.state; igT[s] = rh.get_integ(env)
+        if s % 64 == 0:
+            print("batch env", s, flush=True)
+    for t in range(H):
+        obs_crc[t] = zlib.crc32(obs_all[t].tobytes())
+    _save("batch512.npz", state0=st0, params=par, goal=goal, stateT=stT, integT=igT, reward=reward, done=done,
+          nfev=nfev, obs_crc=obs_crc, obs_last=obs_all[-1], actions_crc=np.uint32(zlib.crc32(actions.tobytes())))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["step", "kat1", "reset", "quad", "batch"]
+    for w in which:
+        {"step": make_step, "kat1": make_kat1, "reset": make_reset, "quad": make_quad, "batch": make_batch}[w]()
