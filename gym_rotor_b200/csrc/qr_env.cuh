@@ -1,0 +1,377 @@
+// qr_env.cuh -- per-env pieces around the integrator: action maps, observation + integral errors,
+// reward / termination, Philox resets and the mode-0 goal generator.  One env per thread, registers only.
+//
+// Reference semantics restated (paths relative to the gym-rotor tree):
+//   action wrappers .............. gym_rotor/envs/quad.py:225-242, wrappers/coupled_yaw_wrapper.py:44-53,
+//                                  wrappers/decoupled_yaw_wrapper.py:49-59, 68-73
+//   get_norm_error_state ......... gym_rotor/envs/quad.py:421-466; quad_utils.py:20-26, 38-63; wrapper_utils.py:3-28
+//   reward / done ................ coupled_yaw_wrapper.py:78-110, decoupled_yaw_wrapper.py:92-140, quad.py:150-166, 274-318
+//   reset ........................ quad.py:171-222, 338-404; coupled_yaw_wrapper.py:27-41
+//   goal generator, mode 0 ....... utils/trajectory_generator.py:113-173, 196-221
+#pragma once
+#include "qr_dop853.cuh"
+
+namespace qr {
+
+// ---- arithmetic that must NOT be contracted into FMAs (numpy evaluates these op by op) --------------
+template <typename T> struct rn;
+template <> struct rn<float> {
+    static QR_DEV float mul(float a, float b) { return __fmul_rn(a, b); }
+    static QR_DEV float add(float a, float b) { return __fadd_rn(a, b); }
+    static QR_DEV float sub(float a, float b) { return __fsub_rn(a, b); }
+    static QR_DEV float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct rn<double> {
+    static QR_DEV double mul(double a, double b) { return __dmul_rn(a, b); }
+    static QR_DEV double add(double a, double b) { return __dadd_rn(a, b); }
+    static QR_DEV double sub(double a, double b) { return __dsub_rn(a, b); }
+    static QR_DEV double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+// ---- kernel arguments --------------------------------------------------------------------------------
+template <typename T> struct EnvConst {
+    T dt, g, rtol, atol, x_lim, v_lim, W_lim, eIx_lim, eIb1_lim, sat, alpha, beta, min_force, euler_lim;
+    float nCx, nCIx, nCv, nCb1, nCIb1, nCW, nCw12, nCW3;   // negated reward coefficients, as float32 (numpy weak scalars)
+    double Cx, Cv, Cb1, CW;                                // base Quad-v0 reward is evaluated in float64
+    double rmin, rmin1, rmin2, udm;
+    int mode, integrator, autoreset, goal_mode, env_type, max_episode_steps, diagnostics;
+};
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) ---------------------------------------------------------------
+struct Philox {
+    uint32_t k0, k1;
+    QR_DEV void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) const
+    {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+// u32 -> uniform in (0,1): (k + 0.5) * 2^-32, exact in double
+QR_DEV double u01(uint32_t k) { return ((double)k + 0.5) * 2.3283064365386963e-10; }
+#define QR_DOMAIN_RESET 0u
+#define QR_DOMAIN_ACTION 0x40000000u
+
+// ---- per-env register state -----------------------------------------------------------------------------
+template <typename T> struct EnvRegs {
+    T x[3];     // position
+    T y[14];    // v(3) | R column-major (9) | W1 W2
+    T W3;
+    T I[8];     // eIx.error(3) eIx.integrand(3) eIb1.error eIb1.integrand
+    T m, d, J1, J3, c_tf, c_tw;
+    T goal[12]; // xd vd b1d Wd
+};
+
+// ---- env.reset(env_type) with counter-based randomness ---------------------------------------------------
+// Uniform order: m d J1 J3 c_tf c_tw | yaw | origin-spawn coin | x(3) | v(3) | W(3) | roll pitch | theta(goal)
+// All reset arithmetic is float64 regardless of T (resets are rare), then cast.
+template <typename T>
+QR_DEV void reset_env(EnvRegs<T>& e, const Philox& ph, uint64_t gid, uint32_t episode, int env_type, double udm, double* theta_out)
+{
+    uint32_t r[20];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) ph((uint32_t)gid, (uint32_t)(gid >> 32), episode, QR_DOMAIN_RESET + j, r + 4 * j);
+    const double m0 = 2.15, d0 = 0.23, J10 = 0.022, J30 = 0.035, ctf0 = 0.0135, ctw0 = 2.2;  // quad.py:28-32
+    double p[6] = {m0, d0, J10, J30, ctf0, ctw0};
+    if (env_type == 0) {
+        double rr = udm / 100.0;
+        const double nom[6] = {m0, d0, J10, J30, ctf0, ctw0};
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double w = (j == 5) ? nom[j] * (rr / 2.) : nom[j] * rr;  // c_tw: half the range (quad.py:375)
+            double lo = nom[j] - w, hi = nom[j] + w;
+            p[j] = lo + (hi - lo) * u01(r[j]);
+        }
+    }
+    const double PI = 3.14159265358979323846;
+    double yaw = -PI + (PI - (-PI)) * u01(r[6]);
+    double ix, iv, iR, iW;
+    if (env_type == 0) {
+        if (u01(r[7]) < 0.2) { ix = 0; iv = 0; iR = 0; iW = 0; }                       // quad.py:342-346
+        else { ix = 0.6; iv = 4.0 * 0.5; iR = 50 * (PI / 180.); iW = 2 * PI * 0.5; }   // quad.py:347-351
+    } else { ix = 0.4; iv = 0; iR = 0; iW = 0; }                                       // quad.py:352-356
+    double xs[3], vs[3], Ws[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        xs[i] = -ix + (ix - (-ix)) * u01(r[8 + i]);
+        vs[i] = -iv + (iv - (-iv)) * u01(r[11 + i]);
+        Ws[i] = -iW + (iW - (-iW)) * u01(r[14 + i]);
+    }
+    double roll = -iR + (iR - (-iR)) * u01(r[17]), pitch = -iR + (iR - (-iR)) * u01(r[18]);
+    double sr, cr, sp, cp, sy, cy;
+    sincos(roll, &sr, &cr); sincos(pitch, &sp, &cp); sincos(yaw, &sy, &cy);
+    // R = Rz(yaw) Ry(pitch) Rx(roll)   (Rotation.from_euler('xyz'), quad.py:199)
+    double R[9] = {cy * cp, sy * cp, -sp,
+                   cy * sp * sr - sy * cr, sy * sp * sr + cy * cr, cp * sr,
+                   cy * sp * cr + sy * sr, sy * sp * cr - cy * sr, cp * cr};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { e.x[i] = (T)xs[i]; e.y[i] = (T)vs[i]; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) e.y[3 + i] = (T)R[i];
+    e.y[12] = (T)Ws[0]; e.y[13] = (T)Ws[1]; e.W3 = (T)Ws[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e.I[i] = (T)0;
+    e.m = (T)p[0]; e.d = (T)p[1]; e.J1 = (T)p[2]; e.J3 = (T)p[3]; e.c_tf = (T)p[4]; e.c_tw = (T)p[5];
+    *theta_out = (-25.0 + 50.0 * u01(r[19])) * (PI / 180.);   // trajectory_generator.py:144
+}
+
+// ---- goal generator, mode 0 ---------------------------------------------------------------------------------
+// Wd = [0, 0, b3 . (b1c x b1c_dot)] with b1d_dot = 0 (trajectory_generator.py:165-172)
+template <typename T> QR_DEV void traj_wd(const T* R, const T* W, const T* b1d, T* Wd)
+{
+    const T* b3 = R + 6;
+    // b3_dot = R hat(W) e3
+    T b3d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b3d[i] = R[i] * W[1] - R[i + 3] * W[0];
+    T dp = b1d[0] * b3[0] + b1d[1] * b3[1] + b1d[2] * b3[2];
+    T dq = b1d[0] * b3d[0] + b1d[1] * b3d[1] + b1d[2] * b3d[2];
+    T b1c[3], b1cd[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        b1c[i] = b1d[i] - dp * b3[i];
+        b1cd[i] = (T)0 - (((T)0 * b3[i] + dq * b3[i]) + dp * b3d[i]);
+    }
+    T oc0 = b1c[1] * b1cd[2] - b1c[2] * b1cd[1];
+    T oc1 = b1c[2] * b1cd[0] - b1c[0] * b1cd[2];
+    T oc2 = b1c[0] * b1cd[1] - b1c[1] * b1cd[0];
+    Wd[0] = 0; Wd[1] = 0; Wd[2] = b3[0] * oc0 + b3[1] * oc1 + b3[2] * oc2;
+}
+
+// mark_traj_start + first get_desired(mode 0) on the float32-cast reset state (main.py:226-229):
+// xd = vd = 0, b1d = Rz(theta) [cos psi, sin psi, 0], psi = heading of b1; Wd from that same f32 state.
+template <typename T> QR_DEV void init_goal_mode0(EnvRegs<T>& e, double theta)
+{
+    double R[9], W[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = (double)(float)e.y[3 + i];
+    W[0] = (double)(float)e.y[12]; W[1] = (double)(float)e.y[13]; W[2] = (double)(float)e.W3;
+    ensure_so3<double>(R);
+    double psi = atan2(R[1], R[0]);
+    double cps = cos(psi), sps = sin(psi), cth = cos(theta), sth = sin(theta);
+    double b1d[3] = {cth * cps - sth * sps, sth * cps + cth * sps, 0.0};
+    double Wd[3];
+    traj_wd<double>(R, W, b1d, Wd);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        e.goal[i] = 0; e.goal[3 + i] = 0; e.goal[6 + i] = (T)b1d[i]; e.goal[9 + i] = (T)Wd[i];
+    }
+}
+
+// ---- get_norm_error_state ------------------------------------------------------------------------------------
+// Writes the float32 observation (COUPLED 23, DECOUPLED 15+3) and advances the integral errors once.
+template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<T>& c, float* o)
+{
+    using N = num<T>;
+    using A = rn<T>;
+    T R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = e.y[3 + i];
+    int fl = ensure_so3<T>(R);   // state_normalization (quad_utils.py:20-26)
+    const T W[3] = {e.y[12], e.y[13], e.W3};
+    T ex[3], ev[3], eW[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ex[i] = A::sub(A::div(e.x[i], c.x_lim), A::div(e.goal[i], c.x_lim));
+        ev[i] = A::sub(A::div(e.y[i], c.v_lim), A::div(e.goal[3 + i], c.v_lim));
+        eW[i] = A::sub(A::div(W[i], c.W_lim), A::div(e.goal[9 + i], c.W_lim));
+    }
+    const T* b1 = R; const T* b2 = R + 3; const T* b3 = R + 6;
+    const T* b1d = e.goal + 6;
+    // numpy's 3-vector dot is an FMA chain (OpenBLAS ddot)
+    T d3 = N::fma(b1d[2], b3[2], N::fma(b1d[1], b3[1], A::mul(b1d[0], b3[0])));
+    T b1c[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b1c[i] = A::sub(b1d[i], A::mul(d3, b3[i]));
+    T dn = N::fma(b1c[2], b2[2], N::fma(b1c[1], b2[1], A::mul(b1c[0], b2[0])));
+    T dd = N::fma(b1c[2], b1[2], N::fma(b1c[1], b1[1], A::mul(b1c[0], b1[0])));
+    const T PI = (T)3.14159265358979323846;
+    T eb1n = A::div(N::atan2(-dn, dd), PI);
+    T eIxn[3], eIb1n;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        T gnew = A::add(A::mul(-c.alpha, e.I[i]), A::mul(ex[i], c.x_lim));
+        e.I[i] = A::add(e.I[i], A::div(A::mul(A::add(e.I[3 + i], gnew), c.dt), (T)2));
+        e.I[3 + i] = gnew;
+        T q = A::div(e.I[i], c.eIx_lim);
+        eIxn[i] = q < -c.sat ? -c.sat : (q > c.sat ? c.sat : q);
+    }
+    {
+        T gnew = A::add(A::mul(-c.beta, e.I[6]), A::mul(eb1n, PI));
+        e.I[6] = A::add(e.I[6], A::div(A::mul(A::add(e.I[7], gnew), c.dt), (T)2));
+        e.I[7] = gnew;
+        T q = A::div(e.I[6], c.eIb1_lim);
+        eIb1n = q < -c.sat ? -c.sat : (q > c.sat ? c.sat : q);
+    }
+    if (c.mode == 2) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            o[i] = (float)ex[i]; o[3 + i] = (float)eIxn[i]; o[6 + i] = (float)ev[i]; o[9 + i] = (float)b3[i];
+            o[12 + i] = (float)A::add(A::mul(eW[0], b1[i]), A::mul(eW[1], b2[i]));
+        }
+        o[15] = (float)eb1n; o[16] = (float)eIb1n; o[17] = (float)eW[2];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            o[i] = (float)ex[i]; o[3 + i] = (float)eIxn[i]; o[6 + i] = (float)ev[i]; o[20 + i] = (float)eW[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[9 + i] = (float)R[i];
+        o[18] = (float)eb1n; o[19] = (float)eIb1n;
+    }
+    return fl;
+}
+
+// ---- reward and termination on the float32 observation --------------------------------------------------------
+// numpy: norm(v,2) of a float32 3-vector = sqrtf(float(double-accumulated float32 products)) (OpenBLAS sdot);
+// `**2` restated as a correctly rounded square (numpy's powf(x,2) differs by 1 ulp in ~0.07 % of cases).
+QR_DEV float norm2sq_f32(const float* v)
+{
+    double s = (double)__fmul_rn(v[0], v[0]) + (double)__fmul_rn(v[1], v[1]) + (double)__fmul_rn(v[2], v[2]);
+    float n = __fsqrt_rn((float)s);
+    return __fmul_rn(n, n);
+}
+QR_DEV double interp01(double r, double rmin)
+{
+    // np.interp(r, [rmin, 0], [0, 1])
+    if (r != r) return r;
+    if (r <= rmin) return 0.0;
+    if (r >= 0.0) return 1.0;
+    return __dadd_rn(__dmul_rn(1.0 / (0.0 - rmin), __dsub_rn(r, rmin)), 0.0);
+}
+
+template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float* o, double* rew, int* dn)
+{
+    dn[0] = 0; dn[1] = 0;
+    if (c.mode == 1) {
+        float rx = __fmul_rn(c.nCx, norm2sq_f32(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32(o + 3));
+        float rv = __fmul_rn(c.nCv, norm2sq_f32(o + 6)), rw = __fmul_rn(c.nCW, norm2sq_f32(o + 20));
+        float a18 = fabsf(o[18]), a19 = fabsf(o[19]);
+        float rb = __fmul_rn(c.nCb1, a18), rib = __fmul_rn(c.nCIb1, __fmul_rn(a19, a19));
+        float r = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(rx, rix), rv), rb), rib), rw);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[20 + i]) >= 1.0f) dn[0] = 1;
+        rew[0] = dn[0] ? -1.0 : interp01((double)r, c.rmin);
+        rew[1] = 0.0;
+    } else {
+        float rx = __fmul_rn(c.nCx, norm2sq_f32(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32(o + 3));
+        float rv = __fmul_rn(c.nCv, norm2sq_f32(o + 6)), rw = __fmul_rn(c.nCw12, norm2sq_f32(o + 12));
+        float r1 = __fadd_rn(__fadd_rn(__fadd_rn(rx, rix), rv), rw);
+        float a0 = fabsf(o[15]), a1 = fabsf(o[16]), a2 = fabsf(o[17]);
+        float r2 = __fadd_rn(__fadd_rn(__fmul_rn(c.nCb1, a0), __fmul_rn(c.nCIb1, __fmul_rn(a1, a1))),
+                             __fmul_rn(c.nCW3, __fmul_rn(a2, a2)));
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[12 + i]) >= 1.0f) dn[0] = 1;
+        if (a2 >= 1.0f) dn[1] = 1;
+        rew[0] = dn[0] ? -1.0 : interp01((double)r1, c.rmin1);
+        rew[1] = dn[1] ? -1.0 : interp01((double)r2, c.rmin2);
+    }
+}
+
+// Base Quad-v0 reward / done on the float64 next state (quad.py:274-318)
+template <typename T> QR_DEV void reward_done_quad(const EnvRegs<T>& e, const EnvConst<T>& c, double* rew, int* dn)
+{
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = (double)e.y[3 + i];
+    ensure_so3<double>(R);
+    const double W[3] = {(double)e.y[12], (double)e.y[13], (double)e.W3};
+    double eX2 = 0, eV2 = 0, W2 = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double a = (double)e.x[i] - (double)e.goal[i], b = (double)e.y[i] - (double)e.goal[3 + i];
+        eX2 = fma(a, a, eX2); eV2 = fma(b, b, eV2); W2 = fma(W[i], W[i], W2);
+    }
+    double nx = sqrt(eX2), nv = sqrt(eV2), nw = sqrt(W2);
+    double th = atan2(R[1], R[0]);
+    double cb[3] = {cos(th), sin(th), 0.0};
+    double b1d[3] = {(double)e.goal[6], (double)e.goal[7], (double)e.goal[8]};
+    double nd = sqrt(fma(b1d[2], b1d[2], fma(b1d[1], b1d[1], b1d[0] * b1d[0])));
+    double nc = sqrt(fma(cb[2], cb[2], fma(cb[1], cb[1], cb[0] * cb[0])));
+    double du[3] = {b1d[0] / nd, b1d[1] / nd, b1d[2] / nd}, cu[3] = {cb[0] / nc, cb[1] / nc, cb[2] / nc};
+    double dp = fma(du[2], cu[2], fma(du[1], cu[1], du[0] * cu[0]));
+    dp = dp < -1 ? -1 : (dp > 1 ? 1 : dp);
+    double ang = acos(dp);
+    if (du[0] * cu[1] - du[1] * cu[0] < 0) ang = -ang;
+    double eb1 = ang / 3.14159265358979323846;
+    double r = 0.0 + (((-c.Cx * (nx * nx) + -c.Cb1 * fabs(eb1)) + -c.Cv * (nv * nv)) + -c.CW * (nw * nw));
+    const double R2D = 180.0 / 3.14159265358979323846;
+    double roll = atan2(R[5], R[8]) * R2D;
+    double pitch = atan2(-R[2], sqrt(R[0] * R[0] + R[1] * R[1])) * R2D;
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (fabs((double)e.x[i]) >= (double)c.x_lim) d = 1;
+        if (fabs((double)e.y[i]) >= (double)c.v_lim) d = 1;
+        if (fabs(W[i]) >= (double)c.W_lim) d = 1;
+    }
+    if (fabs(roll) >= (double)c.euler_lim || fabs(pitch) >= (double)c.euler_lim) d = 1;
+    dn[0] = d; dn[1] = 0;
+    rew[0] = d ? -1.0 : interp01(r, c.rmin);
+    rew[1] = 0.0;
+}
+
+// ---- action wrappers -> thrust f and moment M -----------------------------------------------------------------
+// a[]: normalised action (already converted to T); act_f32: the caller's array was float32, in which case
+// numpy evaluates the thrust scaling in float32 (python-float * np.float32 -> float32, NEP 50).
+template <typename T>
+QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, bool act_f32, T& f, T* M)
+{
+    using A = rn<T>;
+    using N = num<T>;
+    const T hover = A::div(A::mul(e.m, c.g), (T)4);           // quad.py:390
+    const T maxf = A::mul(e.c_tw, hover);                     // quad.py:392
+    const T avrg = A::div(A::add(c.min_force, maxf), (T)2);   // quad.py:403
+    const T scale = A::sub(maxf, avrg);                       // quad.py:404
+    if (c.mode == 0) {
+        T Tm[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (act_f32 && sizeof(T) == 8) {
+                float tv = __fadd_rn(__fmul_rn((float)scale, (float)a[i]), (float)avrg);
+                tv = tv < (float)c.min_force ? (float)c.min_force : (tv > (float)maxf ? (float)maxf : tv);
+                Tm[i] = (T)tv;
+            } else {
+                T tv = A::add(A::mul(scale, a[i]), avrg);
+                Tm[i] = tv < c.min_force ? c.min_force : (tv > maxf ? maxf : tv);
+            }
+        }
+        f = A::add(A::add(A::add(Tm[0], Tm[1]), Tm[2]), Tm[3]);   // forces_to_fM @ T, quad.py:396-401,238
+        M[0] = A::add(A::mul(-e.d, Tm[1]), A::mul(e.d, Tm[3]));
+        M[1] = A::add(A::mul(e.d, Tm[0]), A::mul(-e.d, Tm[2]));
+        M[2] = A::add(A::add(A::add(A::mul(-e.c_tf, Tm[0]), A::mul(e.c_tf, Tm[1])), A::mul(-e.c_tf, Tm[2])), A::mul(e.c_tf, Tm[3]));
+        return;
+    }
+    if (act_f32 && sizeof(T) == 8) {
+        float fv = __fmul_rn(4.0f, __fadd_rn(__fmul_rn((float)scale, (float)a[0]), (float)avrg));
+        float lo = (float)A::mul((T)4, c.min_force), hi = (float)A::mul((T)4, maxf);
+        fv = fv < lo ? lo : (fv > hi ? hi : fv);
+        f = (T)fv;
+    } else {
+        T fv = A::mul((T)4, A::add(A::mul(scale, a[0]), avrg));
+        T lo = A::mul((T)4, c.min_force), hi = A::mul((T)4, maxf);
+        f = fv < lo ? lo : (fv > hi ? hi : fv);
+    }
+    if (c.mode == 1) {
+        M[0] = a[1]; M[1] = a[2]; M[2] = a[3];
+    } else {
+        // decoupled:68-73 on the pre-step (already SO(3)-checked) R and W
+        const T* b1 = e.y + 3; const T* b2 = e.y + 6;
+        T t1 = N::fma(b1[2], a[3], N::fma(b1[1], a[2], A::mul(b1[0], a[1])));
+        T t2 = N::fma(b2[2], a[3], N::fma(b2[1], a[2], A::mul(b2[0], a[1])));
+        M[0] = A::add(t1, A::mul(A::mul(e.J3, e.W3), e.y[13]));
+        M[1] = A::sub(t2, A::mul(A::mul(e.J3, e.W3), e.y[12]));
+        M[2] = a[4];
+    }
+}
+
+}  // namespace qr

@@ -1,0 +1,162 @@
+// qr_math.cuh -- scalar-type traits and small SO(3) helpers for the step kernels (sm_100a).
+//
+// Reference semantics restated here (never copied):
+//   ensure_SO3 / psvd ........ gym_rotor/envs/quad_utils.py:123-142, 226-240
+//   hat ...................... gym_rotor/envs/quad_utils.py:80-85
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define QR_DEV __device__ __forceinline__
+
+namespace qr {
+
+template <typename T> struct num;
+
+template <> struct num<float> {
+    static QR_DEV float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    static QR_DEV float abs(float a) { return fabsf(a); }
+    static QR_DEV float sqrt(float a) { return sqrtf(a); }
+    static QR_DEV float rsqrt(float a) { return rsqrtf(a); }
+    static QR_DEV float max(float a, float b) { return fmaxf(a, b); }
+    static QR_DEV float min(float a, float b) { return fminf(a, b); }
+    static QR_DEV float atan2(float a, float b) { return atan2f(a, b); }
+    static QR_DEV float nextafter(float a, float b) { return nextafterf(a, b); }
+    static QR_DEV float inf() { return __int_as_float(0x7f800000); }
+    // x^(1/8) and x^(-1/8) by square-root chains: <= 2 ulp, no transcendental (only scales the step size)
+    static QR_DEV float root8(float x) { return sqrtf(sqrtf(sqrtf(x))); }
+    static QR_DEV float inv_root8(float x) { return rsqrtf(sqrtf(sqrtf(x))); }
+    static QR_DEV float recip(float x) { return 1.0f / x; }
+    static constexpr float eps_jacobi = 1e-7f;
+    static constexpr float huge = 3.0e38f;
+};
+
+template <> struct num<double> {
+    static QR_DEV double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    static QR_DEV double abs(double a) { return fabs(a); }
+    static QR_DEV double sqrt(double a) { return ::sqrt(a); }
+    static QR_DEV double rsqrt(double a) { return 1.0 / ::sqrt(a); }
+    static QR_DEV double max(double a, double b) { return fmax(a, b); }
+    static QR_DEV double min(double a, double b) { return fmin(a, b); }
+    static QR_DEV double atan2(double a, double b) { return ::atan2(a, b); }
+    static QR_DEV double nextafter(double a, double b) { return ::nextafter(a, b); }
+    static QR_DEV double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static QR_DEV double root8(double x) { return ::sqrt(::sqrt(::sqrt(x))); }
+    static QR_DEV double inv_root8(double x) { return 1.0 / ::sqrt(::sqrt(::sqrt(x))); }
+    static QR_DEV double recip(double x) { return 1.0 / x; }
+    static constexpr double eps_jacobi = 1e-16;
+    static constexpr double huge = 1.0e300;
+};
+
+// R is column-major: R[i + 3*j] = R_ij, i.e. R[0..2] = b1, R[3..5] = b2, R[6..8] = b3.
+template <typename T> QR_DEV T det3(const T* A)
+{
+    return A[0] * (A[4] * A[8] - A[7] * A[5]) - A[3] * (A[1] * A[8] - A[7] * A[2]) + A[6] * (A[1] * A[5] - A[4] * A[2]);
+}
+
+// The acceptance test of ensure_SO3 (quad_utils.py:133-136):
+//   np.allclose(R.T@R, I, rtol=1e-5, atol=1e-5)  <=> |RtR_ij - I_ij| <= 1e-5 + 1e-5*I_ij   (diag 2e-5, off-diag 1e-5)
+//   np.isclose(det R, 1, rtol=1e-5)              <=> |det - 1| <= 1e-8 + 1e-5
+// NaNs fail every comparison, exactly like numpy.  This runs inside EVERY right-hand-side evaluation
+// (state_decomposition, quad_utils.py:12-16), so it is written branch-free: one predicate at the end.
+template <typename T> QR_DEV bool so3_ok(const T* R)
+{
+    using N = num<T>;
+    const T tol = (T)1e-5;
+    T d00 = N::fma(R[2], R[2], N::fma(R[1], R[1], R[0] * R[0]));
+    T d11 = N::fma(R[5], R[5], N::fma(R[4], R[4], R[3] * R[3]));
+    T d22 = N::fma(R[8], R[8], N::fma(R[7], R[7], R[6] * R[6]));
+    T d01 = N::fma(R[2], R[5], N::fma(R[1], R[4], R[0] * R[3]));
+    T d02 = N::fma(R[2], R[8], N::fma(R[1], R[7], R[0] * R[6]));
+    T d12 = N::fma(R[5], R[8], N::fma(R[4], R[7], R[3] * R[6]));
+    T dg = N::max(N::max(N::abs(d00 - (T)1), N::abs(d11 - (T)1)), N::abs(d22 - (T)1));
+    T od = N::max(N::max(N::abs(d01), N::abs(d02)), N::abs(d12));
+    T dt = N::abs(det3(R) - (T)1);
+    // fmax drops NaNs, so test finiteness through a sum that propagates them
+    T nanprobe = (d00 + d11 + d22) + (d01 + d02 + d12);
+    return (dg <= tol + tol) && (od <= tol) && (dt <= (T)1e-8 + tol) && (nanprobe == nanprobe);
+}
+
+// psvd + "U @ VT.T" (quad_utils.py:138-140, 226-240): R <- U diag(1,1,det U det Vt) Vt by one-sided
+// Jacobi.  Rare path (only the Euler probe of the initial-step selection leaves SO(3) by > 1e-5), kept
+// out of line so that it does not add register pressure to the integrator.  Returns 1 on failure.
+template <typename T> __device__ __noinline__ int project_so3(T* R)
+{
+    using N = num<T>;
+    T A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; ++i) {
+        A[i] = R[i];
+        if (!(N::abs(A[i]) <= N::huge)) return 1;
+    }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        int rotated = 0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                T al = 0, be = 0, ga = 0;
+                for (int k = 0; k < 3; ++k) {
+                    al += A[k + 3 * p] * A[k + 3 * p];
+                    be += A[k + 3 * q] * A[k + 3 * q];
+                    ga += A[k + 3 * p] * A[k + 3 * q];
+                }
+                if (N::abs(ga) <= N::eps_jacobi * N::sqrt(al * be) || ga == 0) continue;
+                rotated = 1;
+                T zeta = (be - al) / ((T)2 * ga);
+                T t = (zeta >= 0 ? (T)1 : (T)-1) / (N::abs(zeta) + N::sqrt((T)1 + zeta * zeta));
+                T c = (T)1 / N::sqrt((T)1 + t * t), s = c * t;
+                for (int k = 0; k < 3; ++k) {
+                    T ap = A[k + 3 * p], aq = A[k + 3 * q];
+                    A[k + 3 * p] = c * ap - s * aq;
+                    A[k + 3 * q] = s * ap + c * aq;
+                    T vp = V[k + 3 * p], vq = V[k + 3 * q];
+                    V[k + 3 * p] = c * vp - s * vq;
+                    V[k + 3 * q] = s * vp + c * vq;
+                }
+            }
+        if (!rotated) break;
+    }
+    T sig[3], U[9];
+    int bad = 0, jmin = 0;
+    for (int j = 0; j < 3; ++j) {
+        sig[j] = N::sqrt(A[3 * j] * A[3 * j] + A[1 + 3 * j] * A[1 + 3 * j] + A[2 + 3 * j] * A[2 + 3 * j]);
+        if (sig[j] < sig[jmin]) jmin = j;
+    }
+    for (int j = 0; j < 3; ++j) {
+        if (!(sig[j] > 0)) { bad = 1; for (int k = 0; k < 3; ++k) U[k + 3 * j] = 0; continue; }
+        for (int k = 0; k < 3; ++k) U[k + 3 * j] = A[k + 3 * j] / sig[j];
+    }
+    if (bad) {
+        int a = (jmin + 1) % 3, b = (jmin + 2) % 3;
+        if (!(sig[a] > 0) || !(sig[b] > 0)) return 1;
+        U[0 + 3 * jmin] = U[1 + 3 * a] * U[2 + 3 * b] - U[2 + 3 * a] * U[1 + 3 * b];
+        U[1 + 3 * jmin] = U[2 + 3 * a] * U[0 + 3 * b] - U[0 + 3 * a] * U[2 + 3 * b];
+        U[2 + 3 * jmin] = U[0 + 3 * a] * U[1 + 3 * b] - U[1 + 3 * a] * U[0 + 3 * b];
+    }
+    T sgn = det3(U) * det3(V);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            T s = 0;
+            for (int k = 0; k < 3; ++k) {
+                T u = U[i + 3 * k];
+                if (k == jmin) u *= sgn;
+                s += u * V[j + 3 * k];
+            }
+            R[i + 3 * j] = s;
+        }
+    return bad;
+}
+
+// ensure_SO3 on a register-resident R; flags: bit0 = projected, bit1 = projection failed
+template <typename T> QR_DEV int ensure_so3(T* R)
+{
+    if (so3_ok(R)) return 0;
+    T tmp[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tmp[i] = R[i];
+    int bad = project_so3<T>(tmp);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = tmp[i];
+    return 1 | (bad << 1);
+}
+
+}  // namespace qr

@@ -1,0 +1,292 @@
+"""Batched, device-resident mirror of gym-rotor's env objects.
+
+`BatchedQuadEnv` keeps the reference's duck-typed surface -- reset / step / get_current_state /
+set_goal_state / get_norm_error_state and the attributes the trainer reads (main.py:68-73,126-129,145-147,
+164,226-230; policy_regularization.py:31-33) -- but every method works on N envs whose state lives on the
+GPU.  All compute happens in the sm_100a library behind include/quadrotor_b200.h; torch is used for
+device tensors and streams only.  There is no CPU path.
+
+Shapes: obs MONO [N,23] / MODUL ([N,15],[N,3]) float32; reward, done [N,G]; state [N,18].
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_FRAMEWORKS = {"QUAD": nat.MODE_QUAD, "MONO": nat.MODE_COUPLED, "MODUL": nat.MODE_DECOUPLED}
+
+
+class _DevArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _view(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+class BatchedQuadEnv:
+    """N quadrotor envs on one GPU.  `framework`: 'MONO' (CoupledWrapper), 'MODUL' (DecoupledWrapper), 'QUAD' (Quad-v0)."""
+
+    def __init__(self, num_envs, framework="MONO", dtype=torch.float32, device="cuda:0", seed=1992, autoreset=False,
+                 goal_mode="external", env_type="train", max_episode_steps=0, env_id_offset=0, diagnostics=True,
+                 integrator="solve_ivp", **overrides):
+        if not torch.cuda.is_available():
+            raise nat.NativeError("BatchedQuadEnv needs a CUDA device: the simulator has no CPU path")
+        self._L = nat.load()
+        self.framework = framework
+        self.device = torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.dtype = dtype
+        cfg = nat.QrConfig()
+        nat.check(self._L.qr_default_config(C.byref(cfg), _FRAMEWORKS[framework], nat.F64 if dtype == torch.float64 else nat.F32))
+        cfg.n_envs = int(num_envs); cfg.env_id_offset = int(env_id_offset); cfg.seed = int(seed)
+        cfg.autoreset = int(bool(autoreset))
+        cfg.goal_mode = {"external": nat.GOAL_EXTERNAL, "traj0": nat.GOAL_TRAJ_MODE0}[goal_mode]
+        cfg.env_type = nat.ENV_TRAIN if env_type == "train" else nat.ENV_EVAL
+        cfg.max_episode_steps = int(max_episode_steps)
+        cfg.diagnostics = int(bool(diagnostics))
+        cfg.integrator = nat.INT_EULER if integrator == "euler" else nat.INT_DOP853
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError("unknown config field %r" % k)
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        nat.check(self._L.qr_create(C.byref(cfg), self._dev_index, C.byref(self._h)))
+        b = nat.QrBuffers()
+        nat.check(self._L.qr_get_buffers(self._h, C.byref(b)))
+        self._b = b
+        N, O, G = int(num_envs), b.obs_dim, b.n_agents
+        self.num_envs, self.obs_dim, self.act_dim, self.n_agents = N, O, b.act_dim, G
+        ts = "<f8" if dtype == torch.float64 else "<f4"
+        d = self.device
+        # zero-copy views of the library-owned buffers ([component][env] for the state-side arrays)
+        self.state_soa = _view(b.state, (18, N), ts, d)
+        self.integ_soa = _view(b.integ, (8, N), ts, d)
+        self.params_soa = _view(b.params, (6, N), ts, d)
+        self.goal_soa = _view(b.goal, (12, N), ts, d)
+        self.obs = _view(b.obs, (N, O), "<f4", d)
+        self.reward = _view(b.reward, (N, G), ts, d)
+        self.done = _view(b.done, (N, G), "|u1", d)
+        self.terminated = _view(b.terminated, (N,), "|u1", d)
+        self.truncated = _view(b.truncated, (N,), "|u1", d)
+        self.final_obs = _view(b.final_obs, (N, O), "<f4", d)
+        self.nfev = _view(b.nfev, (N,), "<i4", d)
+        self.status = _view(b.status, (N,), "|u1", d)
+        self.ep_return = _view(b.ep_return, (2, N), ts, d)
+        self.ep_length = _view(b.ep_length, (N,), "<i4", d)
+        self.ep_index = _view(b.ep_index, (N,), "<u4", d) if hasattr(torch, "uint32") else None
+        self.stats_dev = _view(b.stats, (nat.NUM_STATS,), "<f8", d)
+        # constants the reference exposes as attributes
+        self.dt, self.g = cfg.dt, cfg.g
+        self.x_lim, self.v_lim, self.W_lim = cfg.x_lim, cfg.v_lim, cfg.W_lim
+        self.eIx_lim, self.eIb1_lim = cfg.eIx_lim, cfg.eIb1_lim
+        self.min_force = cfg.min_force
+        self.alpha, self.beta = cfg.alpha, cfg.beta
+
+    # ---- reference attribute surface (per-env where domain randomisation makes them per-env) ----
+    @property
+    def hover_force(self):
+        return self.params_soa[0] * self.g / 4.0
+
+    @property
+    def max_force(self):
+        return self.params_soa[5] * self.hover_force
+
+    @property
+    def avrg_act(self):
+        return (self.min_force + self.max_force) / 2.0
+
+    @property
+    def scale_act(self):
+        return self.max_force - self.avrg_act
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _mask_ptr(mask):
+        if mask is None:
+            return None, None
+        m = mask.to(torch.uint8).contiguous()
+        return m, C.c_void_p(m.data_ptr())
+
+    # ---- reference methods, batched ----
+    def reset(self, env_type="train", seed=None, options=None, mask=None):
+        """env.reset(env_type) for all envs (or those in `mask`); returns state [N,18] float32 like the reference."""
+        keep, p = self._mask_ptr(mask)
+        nat.check(self._L.qr_reset(self._h, p, nat.ENV_TRAIN if env_type == "train" else nat.ENV_EVAL, self._stream()))
+        return self.state_soa.t().to(torch.float32)
+
+    def init_goal(self, mask=None):
+        """trajectory_generator mark_traj_start + get_desired(mode 0) (goal_mode='traj0')."""
+        keep, p = self._mask_ptr(mask)
+        nat.check(self._L.qr_init_goal(self._h, p, self._stream()))
+
+    def get_current_state(self):
+        """Live [N,18] view of the device state (the reference returns a live alias too, quad.py:409-410)."""
+        return self.state_soa.t()
+
+    def set_goal_state(self, xd, vd, b1d, b1d_dot, Wd):
+        g = self.goal_soa
+        for k, v in ((0, xd), (3, vd), (6, b1d), (9, Wd)):
+            v = torch.as_tensor(v, dtype=self.dtype, device=self.device)
+            g[k:k + 3] = (v.t() if v.dim() == 2 else v.reshape(3, 1).expand(3, self.num_envs))
+
+    def get_norm_error_state(self, framework=None, mask=None):
+        """Mutating, like the reference: advances the integral terms once (quad.py:447-450)."""
+        keep, p = self._mask_ptr(mask)
+        nat.check(self._L.qr_norm_error_state(self._h, p, self._stream()))
+        return self._split_obs(self.obs)
+
+    def _split_obs(self, o):
+        if self.framework == "MODUL":
+            return [o[:, :15], o[:, 15:18]]
+        return [o]
+
+    def step(self, action):
+        """env.step(action): action [N,A] float32/float64 CUDA tensor (a list of per-agent tensors is concatenated)."""
+        if isinstance(action, (list, tuple)):
+            action = torch.cat([a.reshape(self.num_envs, -1) for a in action], dim=1)
+        if action.dtype not in (torch.float32, torch.float64):
+            action = action.to(torch.float32)
+        if action.device != self.device or not action.is_contiguous():
+            action = action.to(self.device).contiguous()
+        if tuple(action.shape) != (self.num_envs, self.act_dim):
+            raise ValueError("action must have shape (%d, %d)" % (self.num_envs, self.act_dim))
+        nat.check(self._L.qr_step(self._h, C.c_void_p(action.data_ptr()),
+                                  nat.F64 if action.dtype == torch.float64 else nat.F32, self._stream()))
+        return self._split_obs(self.obs), self.reward, self.done.bool(), False, {}
+
+    def rollout(self, n_steps, actions=None, store=False):
+        """n_steps fused env.step() calls in ONE kernel launch (state stays in registers).
+
+        actions: [n_steps,N,A] tensor, or None for in-kernel Philox U(-1,1) actions.
+        store=True returns per-step (obs, reward, done) tensors [n_steps,N,..]."""
+        ap, ad = None, nat.F32
+        if actions is not None:
+            actions = actions.to(self.device).contiguous()
+            assert tuple(actions.shape) == (n_steps, self.num_envs, self.act_dim)
+            ap = C.c_void_p(actions.data_ptr()); ad = nat.F64 if actions.dtype == torch.float64 else nat.F32
+        obs = rew = dn = None
+        po = pr = pd = None
+        if store:
+            obs = torch.empty((n_steps, self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+            rew = torch.empty((n_steps, self.num_envs, self.n_agents), dtype=self.dtype, device=self.device)
+            dn = torch.empty((n_steps, self.num_envs, self.n_agents), dtype=torch.uint8, device=self.device)
+            po, pr, pd = C.c_void_p(obs.data_ptr()), C.c_void_p(rew.data_ptr()), C.c_void_p(dn.data_ptr())
+        nat.check(self._L.qr_rollout(self._h, int(n_steps), ap, ad, po, pr, pd, self._stream()))
+        return obs, rew, dn
+
+    def step_host(self, actions, obs_out=None, reward_out=None, done_out=None):
+        """End-to-end step with HOST buffers (numpy arrays or pinned CPU tensors): H2D + step + D2H."""
+        def ptr(x):
+            if x is None:
+                return None
+            return C.c_void_p(x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data)
+        dt = actions.dtype
+        is64 = dt in (torch.float64, np.float64, np.dtype("float64"))
+        nat.check(self._L.qr_step_host(self._h, ptr(actions), nat.F64 if is64 else nat.F32, ptr(obs_out),
+                                       ptr(reward_out), ptr(done_out)))
+
+    # ---- state injection / extraction (row-major [N,..] float64 host arrays) ----
+    def set_state(self, state=None, integ=None, params=None, goal=None):
+        def arr(a, c):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            assert a.shape == (self.num_envs, c), a.shape
+            return a, C.c_void_p(a.ctypes.data)
+        ks, ps = arr(state, 18); ki, pi = arr(integ, 8); kp, pp = arr(params, 6); kg, pg = arr(goal, 12)
+        torch.cuda.synchronize(self.device)
+        nat.check(self._L.qr_set_state_host(self._h, ps, pi, pp, pg))
+
+    def get_state(self):
+        N = self.num_envs
+        st, ig, pa, gl = (np.empty((N, c), np.float64) for c in (18, 8, 6, 12))
+        torch.cuda.synchronize(self.device)
+        nat.check(self._L.qr_get_state_host(self._h, *(C.c_void_p(a.ctypes.data) for a in (st, ig, pa, gl))))
+        return st, ig, pa, gl
+
+    def stats(self, reset=True):
+        out = (C.c_double * nat.NUM_STATS)()
+        nat.check(self._L.qr_stats(self._h, out, int(reset), self._stream()))
+        return np.array(out[:], dtype=np.float64)
+
+    @staticmethod
+    def launch_count():
+        return int(nat.load().qr_launch_count())
+
+    def render(self):
+        raise NotImplementedError("render() (vpython viewer, quad.py:469-754) is out of scope")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            self._L.qr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CoupledWrapper(BatchedQuadEnv):
+    """Batched CoupledWrapper (monolithic agent: obs 23, act 4) -- wrappers/coupled_yaw_wrapper.py."""
+
+    def __init__(self, num_envs=1, **kw):
+        super().__init__(num_envs, framework="MONO", **kw)
+
+
+class DecoupledWrapper(BatchedQuadEnv):
+    """Batched DecoupledWrapper (two agents: obs 15+3, act 4+1) -- wrappers/decoupled_yaw_wrapper.py."""
+
+    def __init__(self, num_envs=1, **kw):
+        super().__init__(num_envs, framework="MODUL", **kw)
+
+
+class QuadEnv(BatchedQuadEnv):
+    """Batched base Quad-v0 env (T1..T4 actions, obs = state) -- envs/quad.py."""
+
+    def __init__(self, num_envs=1, **kw):
+        super().__init__(num_envs, framework="QUAD", **kw)
+
+
+class QuadVectorEnv:
+    """gymnasium.vector.VectorEnv-shaped facade (gymnasium itself is not installed in this image).
+
+    reset() -> (obs, info); step(actions) -> (obs, reward, terminated, truncated, info) with same-step
+    auto reset done in-kernel: the returned obs of a finished env is the first observation of its next
+    episode (main.py:226-230) and info['final_obs'] holds the terminal one.
+    """
+
+    def __init__(self, num_envs, framework="MONO", max_episode_steps=4000, goal_mode="traj0", **kw):
+        self.env = BatchedQuadEnv(num_envs, framework=framework, autoreset=True, goal_mode=goal_mode,
+                                  max_episode_steps=max_episode_steps, **kw)
+        self.num_envs = num_envs
+        self.single_observation_shape = (self.env.obs_dim,)
+        self.single_action_shape = (self.env.act_dim,)
+        self.is_vector_env = True
+
+    def reset(self, *, seed=None, options=None):
+        e = self.env
+        e.reset(env_type="train" if e.cfg.env_type == nat.ENV_TRAIN else "eval")
+        if e.cfg.goal_mode == nat.GOAL_TRAJ_MODE0:
+            e.init_goal()
+        obs = e.get_norm_error_state()
+        return obs[0] if len(obs) == 1 else obs, {}
+
+    def step(self, actions):
+        e = self.env
+        obs, rew, done, _, _ = e.step(actions)
+        info = {"final_obs": e.final_obs, "done_n": done}
+        return (obs[0] if len(obs) == 1 else obs), rew, e.terminated.bool(), e.truncated.bool(), info
+
+    def close(self):
+        self.env.close()

@@ -1,0 +1,68 @@
+"""CPU-only: the in-tree CUDA library loads and exports every symbol include/quadrotor_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "quadrotor_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qr_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from gym_rotor_b200 import build, _native
+    build.build()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert sorted(_native.EXPORTS) == names, "python binding and header disagree"
+    lib.qr_abi_version.restype = ctypes.c_int
+    assert lib.qr_abi_version() == 1
+
+
+def test_config_struct_layout_matches_header():
+    """qr_default_config writes the reference's constants into the ctypes mirror of qr_config."""
+    from gym_rotor_b200 import _native
+    L = _native.load()
+    c = _native.QrConfig()
+    assert L.qr_default_config(ctypes.byref(c), _native.MODE_DECOUPLED, _native.F64) == 0
+    assert (c.mode, c.dtype, c.n_envs, c.seed) == (2, 1, 1, 1992)
+    assert abs(c.dt - 0.005) < 1e-18 and c.g == 9.81 and c.rtol == 1e-3 and c.atol == 1e-6
+    assert (c.Cx, c.CIx, c.Cv, c.Cw12, c.Cb1, c.CIb1, c.CW3, c.CW) == (6.0, 0.1, 0.4, 0.6, 6.0, 0.1, 0.1, 0.6)
+    assert (c.reward_min, c.reward_min_1, c.reward_min_2) == (-14.0, -8.0, -7.0)   # quad.py:81-88
+    assert (c.alpha, c.beta, c.min_force, c.udm_pct, c.euler_lim_deg) == (0.01, 0.05, 0.5, 10.0, 85.0)
+    assert L.qr_default_config(ctypes.byref(c), 7, 0) != 0
+    assert b"bad arguments" in L.qr_last_error()
+
+
+def test_no_device_fails_loudly():
+    """Without a GPU the product must refuse to run -- there is no CPU fallback."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from gym_rotor_b200 import _native, vec_env
+    with pytest.raises(_native.NativeError):
+        vec_env.BatchedQuadEnv(8)
+    L = _native.load()
+    c = _native.QrConfig()
+    L.qr_default_config(ctypes.byref(c), 1, 0)
+    h = ctypes.c_void_p()
+    rc = L.qr_create(ctypes.byref(c), 0, ctypes.byref(h))
+    assert rc != 0 and b"no CUDA device" in L.qr_last_error()
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under gym_rotor_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "gym_rotor_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "quad_oracle" not in txt and "oracle/" not in txt.replace("under oracle/", ""), f
