@@ -1,5 +1,4 @@
-// qr_dop853.cuh -- rigid-body right-hand side + scipy's DOP853 controller, one env per thread, all
-// stage derivatives resident in registers.
+// qr_dop853.cuh -- rigid-body right-hand side + scipy's DOP853 controller, one env per lane.
 //
 // What is reproduced (reference: coupled_yaw_wrapper.py:63 / decoupled_yaw_wrapper.py:76 / quad.py:265 call
 // scipy.integrate.solve_ivp(method='DOP853') with default tolerances; SCIPY = scipy/integrate/_ivp):
@@ -15,7 +14,12 @@
 //     stage values of x are never formed: x_new and its two error estimates are accumulated on the fly from
 //     the stage velocities.  W3' = M3/J3 is constant (J1 == J2), so W3 needs no stage storage either and
 //     its error estimate is identically zero.  Stage storage is 14 values (v 3, R 9, W12 2) instead of 18.
-//   * Tableau sparsity: stages 1,2 die after stage 4, so at most 10 stage vectors are live.
+//   * Stage derivatives K1..K11 live in SHARED MEMORY ([slot][component][lane], conflict-free 128/64-bit
+//     accesses), K0 in registers; the stage loop is ROLLED with the tableau in constant memory.  A fully
+//     unrolled register version (round-1 capture A) was 206 KB of SASS and instruction-fetch bound.
+//     Tableau sparsity: row s uses K0 and the contiguous range K[jlo(s)..s-1]; K1/K3 and K2/K4 share slots.
+//   * One ATTEMPT is a function: the caller owns the accept/reject loop, so that lanes of a warp that need
+//     a second attempt do not hold back lanes that are ready for their next env (see qr_kernels.cuh).
 //   * F(y_new) is only evaluated when another step follows (t_new < T): scipy evaluates it always but only
 //     uses it as the next step's first stage; the RHS has no side effects.  nfev is still reported as
 //     scipy counts it (2 + 12 per attempt).
@@ -26,21 +30,100 @@
 
 namespace qr {
 
-#define QR_A(s, j) ((T)DOP_A##s##_##j)
+// ---- tableau in constant memory (uniform-indexed loads in the rolled stage loop) ------------------------
+struct Tableau {
+    double A[12][12];
+    double B[12], E5[12], E3[12], C[12];
+};
+struct TableauF {
+    float A[12][12];
+    float B[12], E5[12], E3[12], C[12];
+};
+__constant__ Tableau c_tab64;
+__constant__ TableauF c_tab32;
 
-// linear combinations of stage derivatives K[j][i] for component i, by tableau row
-#define QR_COMB1(K, i) (QR_A(1, 0) * K[0][i])
-#define QR_COMB2(K, i) (N::fma(QR_A(2, 1), K[1][i], QR_A(2, 0) * K[0][i]))
-#define QR_COMB3(K, i) (N::fma(QR_A(3, 2), K[2][i], QR_A(3, 0) * K[0][i]))
-#define QR_COMB4(K, i) (N::fma(QR_A(4, 3), K[3][i], N::fma(QR_A(4, 2), K[2][i], QR_A(4, 0) * K[0][i])))
-#define QR_COMB5(K, i) (N::fma(QR_A(5, 4), K[4][i], N::fma(QR_A(5, 3), K[3][i], QR_A(5, 0) * K[0][i])))
-#define QR_COMB6(K, i) (N::fma(QR_A(6, 5), K[5][i], N::fma(QR_A(6, 4), K[4][i], N::fma(QR_A(6, 3), K[3][i], QR_A(6, 0) * K[0][i]))))
-#define QR_COMB7(K, i) (N::fma(QR_A(7, 6), K[6][i], N::fma(QR_A(7, 5), K[5][i], N::fma(QR_A(7, 4), K[4][i], N::fma(QR_A(7, 3), K[3][i], QR_A(7, 0) * K[0][i])))))
-#define QR_COMB8(K, i) (N::fma(QR_A(8, 7), K[7][i], N::fma(QR_A(8, 6), K[6][i], N::fma(QR_A(8, 5), K[5][i], N::fma(QR_A(8, 4), K[4][i], N::fma(QR_A(8, 3), K[3][i], QR_A(8, 0) * K[0][i]))))))
-#define QR_COMB9(K, i) (N::fma(QR_A(9, 8), K[8][i], N::fma(QR_A(9, 7), K[7][i], N::fma(QR_A(9, 6), K[6][i], N::fma(QR_A(9, 5), K[5][i], N::fma(QR_A(9, 4), K[4][i], N::fma(QR_A(9, 3), K[3][i], QR_A(9, 0) * K[0][i])))))))
-#define QR_COMB10(K, i) (N::fma(QR_A(10, 9), K[9][i], N::fma(QR_A(10, 8), K[8][i], N::fma(QR_A(10, 7), K[7][i], N::fma(QR_A(10, 6), K[6][i], N::fma(QR_A(10, 5), K[5][i], N::fma(QR_A(10, 4), K[4][i], N::fma(QR_A(10, 3), K[3][i], QR_A(10, 0) * K[0][i]))))))))
-#define QR_COMB11(K, i) (N::fma(QR_A(11, 10), K[10][i], N::fma(QR_A(11, 9), K[9][i], N::fma(QR_A(11, 8), K[8][i], N::fma(QR_A(11, 7), K[7][i], N::fma(QR_A(11, 6), K[6][i], N::fma(QR_A(11, 5), K[5][i], N::fma(QR_A(11, 4), K[4][i], N::fma(QR_A(11, 3), K[3][i], QR_A(11, 0) * K[0][i])))))))))
-#define QR_COMB_W(K, i, P) (N::fma((T)P##11, K[11][i], N::fma((T)P##10, K[10][i], N::fma((T)P##9, K[9][i], N::fma((T)P##8, K[8][i], N::fma((T)P##7, K[7][i], N::fma((T)P##6, K[6][i], N::fma((T)P##5, K[5][i], (T)P##0 * K[0][i]))))))))
+inline void fill_tableau(Tableau& t)
+{
+    for (int i = 0; i < 12; ++i) {
+        for (int j = 0; j < 12; ++j) t.A[i][j] = 0;
+        t.B[i] = t.E5[i] = t.E3[i] = t.C[i] = 0;
+    }
+#define QR_SETA(s, j) t.A[s][j] = DOP_A##s##_##j
+    QR_SETA(1, 0); QR_SETA(2, 0); QR_SETA(2, 1); QR_SETA(3, 0); QR_SETA(3, 2); QR_SETA(4, 0); QR_SETA(4, 2); QR_SETA(4, 3);
+    QR_SETA(5, 0); QR_SETA(5, 3); QR_SETA(5, 4); QR_SETA(6, 0); QR_SETA(6, 3); QR_SETA(6, 4); QR_SETA(6, 5);
+    QR_SETA(7, 0); QR_SETA(7, 3); QR_SETA(7, 4); QR_SETA(7, 5); QR_SETA(7, 6);
+    QR_SETA(8, 0); QR_SETA(8, 3); QR_SETA(8, 4); QR_SETA(8, 5); QR_SETA(8, 6); QR_SETA(8, 7);
+    QR_SETA(9, 0); QR_SETA(9, 3); QR_SETA(9, 4); QR_SETA(9, 5); QR_SETA(9, 6); QR_SETA(9, 7); QR_SETA(9, 8);
+    QR_SETA(10, 0); QR_SETA(10, 3); QR_SETA(10, 4); QR_SETA(10, 5); QR_SETA(10, 6); QR_SETA(10, 7); QR_SETA(10, 8); QR_SETA(10, 9);
+    QR_SETA(11, 0); QR_SETA(11, 3); QR_SETA(11, 4); QR_SETA(11, 5); QR_SETA(11, 6); QR_SETA(11, 7); QR_SETA(11, 8); QR_SETA(11, 9); QR_SETA(11, 10);
+#undef QR_SETA
+    t.B[0] = DOP_B0; t.B[5] = DOP_B5; t.B[6] = DOP_B6; t.B[7] = DOP_B7; t.B[8] = DOP_B8; t.B[9] = DOP_B9; t.B[10] = DOP_B10; t.B[11] = DOP_B11;
+    t.E5[0] = DOP_E5_0; t.E5[5] = DOP_E5_5; t.E5[6] = DOP_E5_6; t.E5[7] = DOP_E5_7; t.E5[8] = DOP_E5_8; t.E5[9] = DOP_E5_9; t.E5[10] = DOP_E5_10; t.E5[11] = DOP_E5_11;
+    t.E3[0] = DOP_E3_0; t.E3[5] = DOP_E3_5; t.E3[6] = DOP_E3_6; t.E3[7] = DOP_E3_7; t.E3[8] = DOP_E3_8; t.E3[9] = DOP_E3_9; t.E3[10] = DOP_E3_10; t.E3[11] = DOP_E3_11;
+    t.C[1] = DOP_C1; t.C[2] = DOP_C2; t.C[3] = DOP_C3; t.C[4] = DOP_C4; t.C[5] = DOP_C5; t.C[6] = DOP_C6;
+    t.C[7] = DOP_C7; t.C[8] = DOP_C8; t.C[9] = DOP_C9; t.C[10] = DOP_C10; t.C[11] = DOP_C11;
+}
+
+template <typename T> struct tab;
+template <> struct tab<double> {
+    static QR_DEV double A(int s, int j) { return c_tab64.A[s][j]; }
+    static QR_DEV double B(int j) { return c_tab64.B[j]; }
+    static QR_DEV double E5(int j) { return c_tab64.E5[j]; }
+    static QR_DEV double E3(int j) { return c_tab64.E3[j]; }
+    static QR_DEV double C(int j) { return c_tab64.C[j]; }
+};
+template <> struct tab<float> {
+    static QR_DEV float A(int s, int j) { return c_tab32.A[s][j]; }
+    static QR_DEV float B(int j) { return c_tab32.B[j]; }
+    static QR_DEV float E5(int j) { return c_tab32.E5[j]; }
+    static QR_DEV float E3(int j) { return c_tab32.E3[j]; }
+    static QR_DEV float C(int j) { return c_tab32.C[j]; }
+};
+
+// ---- shared-memory stage storage ----------------------------------------------------------------------------
+// Per warp: KS[slot 0..8][14 components][32 lanes] of T.  Within a slot the 14 components of one lane are
+// packed as 3 x (4 consecutive T) + 1 x (2 consecutive T) so that float accesses are LDS/STS.128 + .64:
+//   element (c, lane): c < 12 -> ((c >> 2) * 32 + lane) * 4 + (c & 3) ;  c >= 12 -> 384 + lane * 2 + (c - 12)
+constexpr int QR_NSLOTS = 9;
+constexpr int QR_SLOT_ELEMS = 14 * 32;
+QR_DEV int k_slot(int j) { return j < 5 ? ((j + 1) & 1) : j - 3; }   // K1,K3 -> 0 ; K2,K4 -> 1 ; K5.. -> 2..8
+
+template <typename T> struct vec4 { T a, b, c, d; };
+template <typename T> struct vec2 { T a, b; };
+
+template <typename T> QR_DEV void ks_load(const T* slot, int lane, T* k)
+{
+    if (sizeof(T) == 4) {
+        const float4* p = reinterpret_cast<const float4*>(slot);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            float4 v = p[g * 32 + lane];
+            k[4 * g] = (T)v.x; k[4 * g + 1] = (T)v.y; k[4 * g + 2] = (T)v.z; k[4 * g + 3] = (T)v.w;
+        }
+        float2 w = reinterpret_cast<const float2*>(slot + 384)[lane];
+        k[12] = (T)w.x; k[13] = (T)w.y;
+    } else {
+        const double2* p = reinterpret_cast<const double2*>(slot);
+#pragma unroll
+        for (int g = 0; g < 7; ++g) {
+            double2 v = p[g * 32 + lane];
+            k[2 * g] = (T)v.x; k[2 * g + 1] = (T)v.y;
+        }
+    }
+}
+template <typename T> QR_DEV void ks_store(T* slot, int lane, const T* k)
+{
+    if (sizeof(T) == 4) {
+        float4* p = reinterpret_cast<float4*>(slot);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) p[g * 32 + lane] = make_float4((float)k[4 * g], (float)k[4 * g + 1], (float)k[4 * g + 2], (float)k[4 * g + 3]);
+        reinterpret_cast<float2*>(slot + 384)[lane] = make_float2((float)k[12], (float)k[13]);
+    } else {
+        double2* p = reinterpret_cast<double2*>(slot);
+#pragma unroll
+        for (int g = 0; g < 7; ++g) p[g * 32 + lane] = make_double2((double)k[2 * g], (double)k[2 * g + 1]);
+    }
+}
 
 // Layout of the 14 integrated components kept in registers: y[0..2] = v, y[3..11] = R (column-major),
 // y[12..13] = W1, W2.  x[3] and W3 are carried separately.
@@ -79,174 +162,192 @@ template <typename T> QR_DEV int rhs14(const T* ys, T W3s, const Dyn<T>& d, T* k
     return fl;
 }
 
-template <typename T> struct StepResult {
-    int nfev;    // as scipy counts: 2 + 12 * attempts
-    int status;  // QR_ST_* bits
-    int nproj;   // SO(3) re-projections that fired inside RHS evaluations
+// Integrator state of one lane between attempts.
+template <typename T> struct OdeLane {
+    T t, h_abs;
+    int rejected;   // a rejection happened inside the current scipy step
+    int nfev;       // as scipy counts: 2 + 12 * attempts
+    int status;     // QR_ST_* bits
+    int nproj;      // SO(3) re-projections inside RHS evaluations
 };
 
-// Integrates (x, y14, W3) over [0, Tend] in place with scipy's DOP853 driver.
+// RungeKutta.__init__: f0 = F(y0) -> K0, then select_initial_step.  (2 RHS evaluations)
 template <typename T>
-QR_DEV StepResult<T> dop853_step(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, const T rtol, const T atol)
+QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T Tend, const T rtol, const T atol, T* K0, OdeLane<T>& o)
 {
     using N = num<T>;
-    StepResult<T> res;
-    res.nfev = 0; res.status = 0; res.nproj = 0;
-    T K[12][14];
-    int fl;
-
-    // ---- RungeKutta.__init__: f0 and select_initial_step --------------------------------------------
-    fl = rhs14<T>(y, W3, d, K[0]); res.nfev++;
-    res.nproj += fl & 1; if (fl & 2) res.status |= 4;
-    T h_abs;
+    o.t = 0; o.rejected = 0; o.nfev = 2; o.status = 0; o.nproj = 0;
+    int fl = rhs14<T>(y, W3, d, K0);
+    o.nproj += fl & 1; if (fl & 2) o.status |= 4;
+    T s0 = 0, s1 = 0;   // sums of (y/sc)^2 and (f0/sc)^2 over all 18 components
+    T isc[14], iscx[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        iscx[i] = N::recip(N::fma(N::abs(x[i]), rtol, atol));
+        T a = x[i] * iscx[i], b = y[i] * iscx[i];   // x' = v
+        s0 = N::fma(a, a, s0); s1 = N::fma(b, b, s1);
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        isc[i] = N::recip(N::fma(N::abs(y[i]), rtol, atol));
+        T a = y[i] * isc[i], b = K0[i] * isc[i];
+        s0 = N::fma(a, a, s0); s1 = N::fma(b, b, s1);
+    }
     {
-        T s0 = 0, s1 = 0;   // sums of (y/sc)^2 and (f0/sc)^2 over all 18 components
-        T isc[14], iscx[3], iscw3;
+        T iscw3 = N::recip(N::fma(N::abs(W3), rtol, atol));
+        T a = W3 * iscw3, b = d.w3dot * iscw3;
+        s0 = N::fma(a, a, s0); s1 = N::fma(b, b, s1);
+    }
+    const T inv_sqrt_n = (T)0.23570226039551584;  // 1/sqrt(18)
+    T d0 = N::sqrt(s0) * inv_sqrt_n, d1 = N::sqrt(s1) * inv_sqrt_n;
+    T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+    h0 = (Tend < h0) ? Tend : h0;   // python min(h0, interval): keeps a NaN h0
+    // Euler probe y1 = y0 + h0 f0 ; f1 = F(y1)
+    T y1[14], k1[14];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            iscx[i] = N::recip(N::fma(N::abs(x[i]), rtol, atol));
-            T a = x[i] * iscx[i], b = y[i] * iscx[i];   // x' = v
-            s0 = N::fma(a, a, s0); s1 = N::fma(b, b, s1);
-        }
+    for (int i = 0; i < 14; ++i) y1[i] = N::fma(h0, K0[i], y[i]);
+    T W31 = N::fma(h0, d.w3dot, W3);
+    fl = rhs14<T>(y1, W31, d, k1);
+    o.nproj += fl & 1; if (fl & 2) o.status |= 4;
+    T s2 = 0;
 #pragma unroll
-        for (int i = 0; i < 14; ++i) {
-            isc[i] = N::recip(N::fma(N::abs(y[i]), rtol, atol));
-            T a = y[i] * isc[i], b = K[0][i] * isc[i];
-            s0 = N::fma(a, a, s0); s1 = N::fma(b, b, s1);
+    for (int i = 0; i < 3; ++i) {   // f1_x - f0_x = v1 - v0
+        T a = (y1[i] - y[i]) * iscx[i];
+        s2 = N::fma(a, a, s2);
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        T a = (k1[i] - K0[i]) * isc[i];
+        s2 = N::fma(a, a, s2);
+    }
+    // the W3 component of f1 - f0 is exactly zero
+    T d2 = N::sqrt(s2) * inv_sqrt_n / h0;
+    T h1;
+    if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = N::max((T)1e-6, h0 * (T)1e-3);
+    else h1 = N::root8((T)0.01 / N::max(d1, d2));
+    T h_abs = (T)100 * h0;
+    h_abs = (h1 < h_abs) ? h1 : h_abs;
+    h_abs = (Tend < h_abs) ? Tend : h_abs;
+    // first _step_impl: h_abs is raised to min_step = 10 ulp(t) if smaller
+    const T min_step = (T)10 * N::abs(N::nextafter((T)0, N::inf()) - (T)0);
+    o.h_abs = (h_abs < min_step) ? min_step : h_abs;
+}
+
+// One attempt of _step_impl (rk.py:125-166) for the lane: 11 stages from K0, y_new, error norm,
+// accept / reject and step-size update.  Returns true when the lane is finished with the whole interval
+// (t reached Tend, or the integrator gave up and keeps the last accepted state).
+// ks: this warp's stage storage, lane: lane id.
+template <typename T>
+QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, const T rtol, const T atol, T* K0,
+                           OdeLane<T>& o, T* ks, const int lane)
+{
+    using N = num<T>;
+    using TB = tab<T>;
+    const T min_step = (T)10 * N::abs(N::nextafter(o.t, N::inf()) - o.t);
+    if (o.h_abs < min_step) { o.status |= 2; return true; }   // TOO_SMALL_STEP: keep the last accepted y
+    T t_new = o.t + o.h_abs;
+    if (t_new - Tend > (T)0) t_new = Tend;
+    const T h = t_new - o.t;
+    o.h_abs = N::abs(h);
+    o.nfev += 12;
+
+    // running sums for x (x' = v): B, E5 and E3 weighted stage velocities
+    T xb[3], x5[3], x3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { xb[i] = TB::B(0) * y[i]; x5[i] = TB::E5(0) * y[i]; x3[i] = TB::E3(0) * y[i]; }
+
+#pragma unroll 1
+    for (int s = 1; s <= 11; ++s) {
+        T acc[14];
+        const T a0 = TB::A(s, 0);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) acc[i] = a0 * K0[i];
+        const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
+#pragma unroll 1
+        for (int j = jlo; j < s; ++j) {
+            const T c = TB::A(s, j);
+            T k[14];
+            ks_load<T>(ks + k_slot(j) * QR_SLOT_ELEMS, lane, k);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) acc[i] = N::fma(c, k[i], acc[i]);
         }
+        T ys[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) ys[i] = N::fma(h, acc[i], y[i]);
+        const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
         {
-            iscw3 = N::recip(N::fma(N::abs(W3), rtol, atol));
-            T a = W3 * iscw3, b = d.w3dot * iscw3;
-            s0 = N::fma(a, a, s0); s1 = N::fma(b, b, s1);
-        }
-        const T inv_sqrt_n = (T)0.23570226039551584;  // 1/sqrt(18)
-        T d0 = N::sqrt(s0) * inv_sqrt_n, d1 = N::sqrt(s1) * inv_sqrt_n;
-        T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
-        h0 = (Tend < h0) ? Tend : h0;   // python min(h0, interval): keeps a NaN h0
-        // Euler probe y1 = y0 + h0 f0 ; f1 = F(y1)
-        T y1[14], k1[14];
-#pragma unroll
-        for (int i = 0; i < 14; ++i) y1[i] = N::fma(h0, K[0][i], y[i]);
-        T W31 = N::fma(h0, d.w3dot, W3);
-        fl = rhs14<T>(y1, W31, d, k1); res.nfev++;
-        res.nproj += fl & 1; if (fl & 2) res.status |= 4;
-        T s2 = 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {   // f1_x - f0_x = v1 - v0
-            T a = (y1[i] - y[i]) * iscx[i];
-            s2 = N::fma(a, a, s2);
-        }
-#pragma unroll
-        for (int i = 0; i < 14; ++i) {
-            T a = (k1[i] - K[0][i]) * isc[i];
-            s2 = N::fma(a, a, s2);
-        }
-        // the W3 component of f1 - f0 is exactly zero
-        T d2 = N::sqrt(s2) * inv_sqrt_n / h0;
-        T h1;
-        if (d1 <= (T)1e-15 && d2 <= (T)1e-15) {
-            h1 = N::max((T)1e-6, h0 * (T)1e-3);
-        } else {
-            h1 = N::root8((T)0.01 / N::max(d1, d2));
-        }
-        h_abs = (T)100 * h0;
-        h_abs = (h1 < h_abs) ? h1 : h_abs;
-        h_abs = (Tend < h_abs) ? Tend : h_abs;
-    }
-
-    // ---- while t < Tend: OdeSolver.step -> _step_impl -----------------------------------------------
-    T t = 0;
-    while (t < Tend) {
-        const T min_step = (T)10 * N::abs(N::nextafter(t, N::inf()) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false;
-        for (;;) {
-            if (h_abs < min_step) { res.status |= 2; return res; }  // TOO_SMALL_STEP: keep last accepted y
-            T t_new = t + h_abs;
-            if (t_new - Tend > (T)0) t_new = Tend;
-            const T h = t_new - t;
-            h_abs = N::abs(h);
-            res.nfev += 12;
-
-            // running sums for x (x' = v): B, E5 and E3 weighted stage velocities
-            T xb[3], x5[3], x3[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { xb[i] = (T)DOP_B0 * y[i]; x5[i] = (T)DOP_E5_0 * y[i]; x3[i] = (T)DOP_E3_0 * y[i]; }
-
-            T ys[14];
-#define QR_STAGE(S, COMB, CS, USE_X, BS, E5S, E3S)                                                         \
-    {                                                                                                      \
-        _Pragma("unroll") for (int i = 0; i < 14; ++i) ys[i] = N::fma(h, COMB(K, i), y[i]);                 \
-        T W3s = N::fma(h * (T)(CS), d.w3dot, W3);                                                           \
-        if (USE_X) {                                                                                       \
-            _Pragma("unroll") for (int i = 0; i < 3; ++i) {                                                 \
-                xb[i] = N::fma((T)(BS), ys[i], xb[i]);                                                      \
-                x5[i] = N::fma((T)(E5S), ys[i], x5[i]);                                                     \
-                x3[i] = N::fma((T)(E3S), ys[i], x3[i]);                                                     \
-            }                                                                                              \
-        }                                                                                                  \
-        fl = rhs14<T>(ys, W3s, d, K[S]);                                                                    \
-        res.nproj += fl & 1; if (fl & 2) res.status |= 4;                                                   \
-    }
-            QR_STAGE(1, QR_COMB1, DOP_C1, 0, 0, 0, 0)
-            QR_STAGE(2, QR_COMB2, DOP_C2, 0, 0, 0, 0)
-            QR_STAGE(3, QR_COMB3, DOP_C3, 0, 0, 0, 0)
-            QR_STAGE(4, QR_COMB4, DOP_C4, 0, 0, 0, 0)
-            QR_STAGE(5, QR_COMB5, DOP_C5, 1, DOP_B5, DOP_E5_5, DOP_E3_5)
-            QR_STAGE(6, QR_COMB6, DOP_C6, 1, DOP_B6, DOP_E5_6, DOP_E3_6)
-            QR_STAGE(7, QR_COMB7, DOP_C7, 1, DOP_B7, DOP_E5_7, DOP_E3_7)
-            QR_STAGE(8, QR_COMB8, DOP_C8, 1, DOP_B8, DOP_E5_8, DOP_E3_8)
-            QR_STAGE(9, QR_COMB9, DOP_C9, 1, DOP_B9, DOP_E5_9, DOP_E3_9)
-            QR_STAGE(10, QR_COMB10, DOP_C10, 1, DOP_B10, DOP_E5_10, DOP_E3_10)
-            QR_STAGE(11, QR_COMB11, DOP_C11, 1, DOP_B11, DOP_E5_11, DOP_E3_11)
-#undef QR_STAGE
-
-            // y_new = y + h * sum_s B_s K_s ; error estimates (rk.py:683-691)
-            T ynew[14], xnew[3];
-            T e5n = 0, e3n = 0;
+            const T bs = TB::B(s), e5s = TB::E5(s), e3s = TB::E3(s);   // zero for s < 5
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                xnew[i] = N::fma(h, xb[i], x[i]);
-                T isc = N::recip(N::fma(N::max(N::abs(x[i]), N::abs(xnew[i])), rtol, atol));
-                T e5 = x5[i] * isc, e3 = x3[i] * isc;
-                e5n = N::fma(e5, e5, e5n); e3n = N::fma(e3, e3, e3n);
+                xb[i] = N::fma(bs, ys[i], xb[i]); x5[i] = N::fma(e5s, ys[i], x5[i]); x3[i] = N::fma(e3s, ys[i], x3[i]);
             }
-#pragma unroll
-            for (int i = 0; i < 14; ++i) {
-                ynew[i] = N::fma(h, QR_COMB_W(K, i, DOP_B), y[i]);
-                T isc = N::recip(N::fma(N::max(N::abs(y[i]), N::abs(ynew[i])), rtol, atol));
-                T e5 = QR_COMB_W(K, i, DOP_E5_) * isc, e3 = QR_COMB_W(K, i, DOP_E3_) * isc;
-                e5n = N::fma(e5, e5, e5n); e3n = N::fma(e3, e3, e3n);
-            }
-            T err;
-            if (e5n == (T)0 && e3n == (T)0) err = 0;
-            else err = N::abs(h) * e5n * N::rsqrt((e5n + (T)0.01 * e3n) * (T)18);
-
-            if (err < (T)1) {
-                // accept
-#pragma unroll
-                for (int i = 0; i < 3; ++i) x[i] = xnew[i];
-#pragma unroll
-                for (int i = 0; i < 14; ++i) y[i] = ynew[i];
-                W3 = N::fma(h, d.w3dot, W3);
-                t = t_new;
-                if (t < Tend) {
-                    T factor = (err == (T)0) ? (T)10 : N::min((T)10, (T)0.9 * N::inv_root8(err));
-                    if (rejected) factor = N::min((T)1, factor);
-                    h_abs *= factor;
-                    fl = rhs14<T>(y, W3, d, K[0]);  // f_new becomes the next step's first stage
-                    res.nproj += fl & 1; if (fl & 2) res.status |= 4;
-                }
-                break;
-            }
-            // A NaN error norm also lands here (nan < 1 is False).  scipy then shrinks h by 0.2 until
-            // TOO_SMALL_STEP and solve_ivp returns the last accepted y; that outcome is produced at once.
-            if (err != err) { res.status |= 1 | 2; return res; }
-            h_abs *= N::max((T)0.2, (T)0.9 * N::inv_root8(err));
-            rejected = true;
         }
+        T kn[14];
+        int fl = rhs14<T>(ys, W3s, d, kn);
+        o.nproj += fl & 1; if (fl & 2) o.status |= 4;
+        ks_store<T>(ks + k_slot(s) * QR_SLOT_ELEMS, lane, kn);
     }
-    return res;
+
+    // y_new = y + h * sum_s B_s K_s ; error estimates (rk.py:683-691)
+    T sb[14], s5[14], s3[14];
+    {
+        const T b0 = TB::B(0), e50 = TB::E5(0), e30 = TB::E3(0);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) { sb[i] = b0 * K0[i]; s5[i] = e50 * K0[i]; s3[i] = e30 * K0[i]; }
+    }
+#pragma unroll 1
+    for (int j = 5; j <= 11; ++j) {
+        const T bj = TB::B(j), e5j = TB::E5(j), e3j = TB::E3(j);
+        T k[14];
+        ks_load<T>(ks + k_slot(j) * QR_SLOT_ELEMS, lane, k);
+#pragma unroll
+        for (int i = 0; i < 14; ++i) { sb[i] = N::fma(bj, k[i], sb[i]); s5[i] = N::fma(e5j, k[i], s5[i]); s3[i] = N::fma(e3j, k[i], s3[i]); }
+    }
+    T e5n = 0, e3n = 0;
+    T xnew[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        xnew[i] = N::fma(h, xb[i], x[i]);
+        T isc = N::recip(N::fma(N::max(N::abs(x[i]), N::abs(xnew[i])), rtol, atol));
+        T e5 = x5[i] * isc, e3 = x3[i] * isc;
+        e5n = N::fma(e5, e5, e5n); e3n = N::fma(e3, e3, e3n);
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        sb[i] = N::fma(h, sb[i], y[i]);   // y_new
+        T isc = N::recip(N::fma(N::max(N::abs(y[i]), N::abs(sb[i])), rtol, atol));
+        T e5 = s5[i] * isc, e3 = s3[i] * isc;
+        e5n = N::fma(e5, e5, e5n); e3n = N::fma(e3, e3, e3n);
+    }
+    T err;
+    if (e5n == (T)0 && e3n == (T)0) err = 0;
+    else err = N::abs(h) * e5n * N::rsqrt((e5n + (T)0.01 * e3n) * (T)18);
+
+    if (err < (T)1) {   // accept
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[i] = xnew[i];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) y[i] = sb[i];
+        W3 = N::fma(h, d.w3dot, W3);
+        o.t = t_new;
+        if (!(o.t < Tend)) return true;
+        T factor = (err == (T)0) ? (T)10 : N::min((T)10, (T)0.9 * N::inv_root8(err));
+        if (o.rejected) factor = N::min((T)1, factor);
+        o.h_abs *= factor;
+        int fl = rhs14<T>(y, W3, d, K0);   // f_new becomes the next step's first stage
+        o.nproj += fl & 1; if (fl & 2) o.status |= 4;
+        // next _step_impl call: fresh rejection flag, h_abs raised to min_step(t) if smaller
+        o.rejected = 0;
+        const T ms = (T)10 * N::abs(N::nextafter(o.t, N::inf()) - o.t);
+        if (o.h_abs < ms) o.h_abs = ms;
+        return false;
+    }
+    // A NaN error norm also lands here (nan < 1 is False).  scipy then shrinks h by 0.2 until TOO_SMALL_STEP
+    // and solve_ivp returns the last accepted y; that outcome is produced at once.
+    if (err != err) { o.status |= 1 | 2; return true; }
+    o.h_abs *= N::max((T)0.2, (T)0.9 * N::inv_root8(err));
+    o.rejected = 1;
+    return false;
 }
 
 }  // namespace qr

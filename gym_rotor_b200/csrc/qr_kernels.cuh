@@ -13,7 +13,8 @@
 
 namespace qr {
 
-constexpr int QR_BLOCK = 128;
+constexpr int QR_BLOCK = 128;        // companion kernels (reset, goal init, observation)
+constexpr int QR_MAX_THREADS = 384;  // step kernel: up to 12 persistent warps per SM
 
 template <typename T> struct StepArgs {
     EnvConst<T> c;
@@ -77,58 +78,274 @@ QR_DEV double warp_sum(double v)
     return v;
 }
 
+// ---- auto reset, out of line (rare: once per episode) ---------------------------------------------------------
+// env.reset -> trajectory_generator.mark_traj_start/get_desired -> set_goal_state -> get_norm_error_state
+// (main.py:226-230).  Works through global memory so that the hot loop's registers are not affected; the
+// caller re-loads the env afterwards.  `o` receives the first observation of the new episode.
+template <typename T>
+__device__ __noinline__ void auto_reset_env(const StepArgs<T>& a, int64_t e, uint32_t episode, float* o)
+{
+    const EnvConst<T>& c = a.c;
+    const Philox ph{a.key0, a.key1};
+    const uint64_t gid = (uint64_t)(a.env_id_offset + e);
+    EnvRegs<T> r;
+    double theta;
+    reset_env<T>(r, ph, gid, episode, c.env_type, c.udm, &theta);
+    if (c.goal_mode == 1) init_goal_mode0<T>(r, theta);
+    else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * a.n + e];
+    }
+    if (c.mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) o[i] = (float)r.x[i];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) o[3 + i] = (float)r.y[i];
+        o[15] = (float)r.y[12]; o[16] = (float)r.y[13]; o[17] = (float)r.W3;
+    } else {
+        norm_error_state<T>(r, c, o);   // first obs of the new episode; advances the integrals once
+    }
+    store_state(r, a, e);
+    store_params_goal(r, a, e, true, c.goal_mode == 1);
+}
+
 struct LocalStats {
     double ret0, ret1, ret0sq, rew0;
     int episodes, length, crashed, truncated, steps, bad, nfev, a1, a2, a3, a4, proj;
 };
 
 // ---- the step kernel ---------------------------------------------------------------------------------------
+// Persistent warps.  Every lane runs the state machine
+//     [A] finish the previous env.step (observation, reward, done, outputs, auto reset) -> take the next
+//         sub-step of the same env or the next env of this warp's sequence -> goal, action, SO(3) check,
+//         f0 and scipy's initial step size
+//     [B] one DOP853 attempt (11 stages through shared memory)
+// and the warp iterates A/B until its envs are exhausted.  A lane whose attempt was rejected or whose first
+// step was shorter than dt simply goes through B again while its neighbours pass through A: the adaptive
+// controller costs the extra attempts it needs (about 6 % under random actions) instead of doubling the
+// work of the whole warp.
+//
+// Warp w of the grid owns the 32-env tiles w, w + W, w + 2W, ... (W = warps in the grid); lanes take
+// consecutive envs from that sequence, so loads and stores of a refill are coalesced.
 template <typename T>
-__global__ void __launch_bounds__(QR_BLOCK) k_step(const StepArgs<T> a)
+__global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
 {
-    extern __shared__ float s_tile[];              // [QR_BLOCK][O] observation staging
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_stats[16];
-    const int tid = threadIdx.x;
-    const int64_t e0 = a.env_lo + (int64_t)blockIdx.x * QR_BLOCK;
-    const int64_t e = e0 + tid;
-    const bool live = e < a.env_hi;
-    const int64_t N = a.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const EnvConst<T>& c = a.c;
     const int O = (c.mode == 1) ? 23 : 18;
     const int A = (c.mode == 2) ? 5 : 4;
     const int G = (c.mode == 2) ? 2 : 1;
+    const int64_t N = a.n;
+    const size_t per_warp = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T) + 32 * 24 * sizeof(float);
+    T* ks = reinterpret_cast<T*>(smem_raw + warp * per_warp);
+    float* os = reinterpret_cast<float*>(smem_raw + warp * per_warp + (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T));
     const Philox ph{a.key0, a.key1};
-    const uint64_t gid = (uint64_t)(a.env_id_offset + e);
 
-    if (tid < 16) s_stats[tid] = 0.0;
+    if (threadIdx.x < 16) s_stats[threadIdx.x] = 0.0;
+    __syncthreads();
 
-    EnvRegs<T> r;
+    // this warp's virtual env sequence
+    const int64_t gw = (int64_t)blockIdx.x * wpb + warp, W = (int64_t)gridDim.x * wpb;
+    const int64_t n_range = a.env_hi - a.env_lo;
+    const int64_t ntiles = (n_range + 31) >> 5;
+    const int64_t my_tiles = (ntiles > gw) ? (ntiles - gw + W - 1) / W : 0;
+    const int64_t vlen = my_tiles << 5;
+    int64_t cursor = 0;   // warp-uniform
+
+    // per-lane persistent state
+    bool busy = false, fin = false, need_init = false;
+    int64_t e = 0;
+    int k = 0;
+    T x[3], y[14], W3 = 0, I[8], K0[14];
+    T p_m = 1, p_d = 0, p_J1 = 1, p_J3 = 1, p_ctf = 0, p_ctw = 1;
+    Dyn<T> d;
+    OdeLane<T> ode;
     T ep_ret[2] = {0, 0};
-    int ep_len = 0;
+    int ep_len = 0, euler_nfev = 0;
     uint32_t ep_idx = 0;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (live) {
-        load_env(r, a, e);
-        ep_ret[0] = a.ep_return[e];
-        if (G == 2) ep_ret[1] = a.ep_return[N + e];
-        ep_len = a.ep_length[e];
-        ep_idx = a.ep_index[e];
-    }
-
-    for (int k = 0; k < a.n_steps; ++k) {
-        float o[23];
-        const bool last = (k == a.n_steps - 1);
-        if (live) {
-            // ---- goal (pre-step state), main.py:145-147 ----
-            if (c.goal_mode == 1) {
-                const T W[3] = {r.y[12], r.y[13], r.W3};
-                T Rg[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) Rg[i] = r.y[3 + i];
-                ensure_so3<T>(Rg);   // get_desired -> state_decomposition
-                traj_wd<T>(Rg, W, r.goal + 6, r.goal + 9);
+    for (int i = 0; i < 3; ++i) x[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) { y[i] = 0; K0[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) I[i] = 0;
+    d.fm = d.g = d.Mi0 = d.Mi1 = d.kw0 = d.kw1 = d.w3dot = 0;
+    ode.t = 0; ode.h_abs = 0; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0;
+
+    for (;;) {
+        // =============================== phase A ===============================
+        // ---- A1: finish the env.step that just completed ----
+        const unsigned finmask = __ballot_sync(0xffffffffu, fin);
+        if (finmask) {
+            const bool last = (k == a.n_steps - 1);
+            bool did_reset = false;
+            if (fin) {
+                float o[23];
+                int st = ode.status;
+                const int nf = (c.integrator == 1 && c.mode == 0) ? euler_nfev : ode.nfev;
+                ls.proj += ode.nproj;
+                EnvRegs<T> r;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) r.x[i] = x[i];
+#pragma unroll
+                for (int i = 0; i < 14; ++i) r.y[i] = y[i];
+                r.W3 = W3;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r.I[i] = I[i];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * N + e];
+                double rew[2]; int dn[2];
+                if (c.mode == 0) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) o[i] = (float)x[i];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) o[3 + i] = (float)y[i];
+                    o[15] = (float)y[12]; o[16] = (float)y[13]; o[17] = (float)W3;
+                    reward_done_quad<T>(r, c, rew, dn);
+                } else {
+                    int fl = norm_error_state<T>(r, c, o);
+                    if (fl & 2) st |= 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) I[i] = r.I[i];
+                    reward_done<T>(c, o, rew, dn);
+                }
+                ep_ret[0] += (T)rew[0]; ep_ret[1] += (T)rew[1];
+                ep_len += 1;
+                const bool term = (dn[0] | dn[1]) != 0;
+                const bool trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
+                ls.steps += 1; ls.nfev += nf; ls.rew0 += rew[0]; ls.bad += (st != 0);
+                { int att = (nf - 2) / 12; ls.a1 += att == 1; ls.a2 += att == 2; ls.a3 += att == 3; ls.a4 += att >= 4; }
+                // per-step scalar outputs
+                T* rw = a.reward_roll ? a.reward_roll + ((int64_t)k * N + e) * G : (last ? a.reward + e * G : nullptr);
+                uint8_t* dd = a.done_roll ? a.done_roll + ((int64_t)k * N + e) * G : (last ? a.done + e * G : nullptr);
+                if (rw) { rw[0] = (T)rew[0]; if (G == 2) rw[1] = (T)rew[1]; }
+                if (dd) { dd[0] = (uint8_t)dn[0]; if (G == 2) dd[1] = (uint8_t)dn[1]; }
+                if (a.reward_roll && last) { a.reward[e * G] = (T)rew[0]; if (G == 2) a.reward[e * G + 1] = (T)rew[1]; }
+                if (a.done_roll && last) { a.done[e * G] = (uint8_t)dn[0]; if (G == 2) a.done[e * G + 1] = (uint8_t)dn[1]; }
+                if (last) { a.terminated[e] = (uint8_t)term; a.truncated[e] = (uint8_t)trunc; }
+                if (c.diagnostics && last) a.nfev[e] = nf;
+                if (st) a.status[e] |= (uint8_t)st;
+                if (c.autoreset && (term || trunc)) {
+                    ls.episodes += 1; ls.length += ep_len; ls.crashed += term; ls.truncated += (trunc && !term);
+                    ls.ret0 += (double)ep_ret[0]; ls.ret1 += (double)ep_ret[1]; ls.ret0sq += (double)ep_ret[0] * (double)ep_ret[0];
+                    if (last) for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
+                    ep_idx += 1;
+                    auto_reset_env<T>(a, e, ep_idx, o);
+                    ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
+                    did_reset = true;
+                }
+                for (int i = 0; i < O; ++i) os[lane * O + i] = o[i];
             }
-            // ---- action ----
+            // ---- observation rows: shared -> global, one 4*O-byte row per finished lane, written by O lanes ----
+            __syncwarp();
+            {
+                float* dst = a.obs_roll ? a.obs_roll + (int64_t)k * N * O : (last ? a.obs : nullptr);
+                // `k` and `last` are per lane; rows are copied with the owner's values broadcast by shuffle
+                unsigned m = finmask;
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int64_t es = __shfl_sync(0xffffffffu, e, src);
+                    const int kk = __shfl_sync(0xffffffffu, k, src);
+                    const bool lst = (kk == a.n_steps - 1);
+                    float* drow = a.obs_roll ? a.obs_roll + ((int64_t)kk * N + es) * O : (lst ? a.obs + es * O : nullptr);
+                    if (lane < O) {
+                        const float v = os[src * O + lane];
+                        if (drow) drow[lane] = v;
+                        if (a.obs_roll && lst) a.obs[es * O + lane] = v;
+                    }
+                }
+                (void)dst;
+            }
+            __syncwarp();
+            if (fin) {
+                fin = false;
+                if (did_reset) {
+                    // re-load what the reset wrote through global memory
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) x[i] = a.state[i * N + e];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) y[i] = a.state[(3 + i) * N + e];
+                    y[12] = a.state[15 * N + e]; y[13] = a.state[16 * N + e]; W3 = a.state[17 * N + e];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) I[i] = a.integ[i * N + e];
+                    p_m = a.params[0 * N + e]; p_d = a.params[1 * N + e]; p_J1 = a.params[2 * N + e];
+                    p_J3 = a.params[3 * N + e]; p_ctf = a.params[4 * N + e]; p_ctw = a.params[5 * N + e];
+                }
+                k += 1;
+                if (k < a.n_steps) need_init = true;
+                else {
+                    // release the env: state back to HBM
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
+                    a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a.integ[i * N + e] = I[i];
+                    a.ep_return[e] = ep_ret[0];
+                    if (G == 2) a.ep_return[N + e] = ep_ret[1];
+                    a.ep_length[e] = ep_len;
+                    a.ep_index[e] = ep_idx;
+                    busy = false;
+                }
+            }
+        }
+        // ---- A2: idle lanes take the next envs of the warp's sequence ----
+        {
+            const unsigned need = __ballot_sync(0xffffffffu, !busy);
+            if (need && cursor < vlen) {
+                const int rank = __popc(need & ((1u << lane) - 1u));
+                const int64_t v = cursor + rank;
+                cursor += __popc(need);
+                if (!busy && v < vlen) {
+                    const int64_t tile = gw + (v >> 5) * W;
+                    const int64_t ee = a.env_lo + (tile << 5) + (v & 31);
+                    if (ee < a.env_hi) {
+                        e = ee; k = 0; busy = true; need_init = true;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) x[i] = a.state[i * N + e];
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) y[i] = a.state[(3 + i) * N + e];
+                        y[12] = a.state[15 * N + e]; y[13] = a.state[16 * N + e]; W3 = a.state[17 * N + e];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) I[i] = a.integ[i * N + e];
+                        p_m = a.params[0 * N + e]; p_d = a.params[1 * N + e]; p_J1 = a.params[2 * N + e];
+                        p_J3 = a.params[3 * N + e]; p_ctf = a.params[4 * N + e]; p_ctw = a.params[5 * N + e];
+                        ep_ret[0] = a.ep_return[e];
+                        ep_ret[1] = (G == 2) ? a.ep_return[N + e] : (T)0;
+                        ep_len = a.ep_length[e];
+                        ep_idx = a.ep_index[e];
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
+        if (busy && need_init) {
+            need_init = false;
+            EnvRegs<T> r;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) r.x[i] = x[i];
+#pragma unroll
+            for (int i = 0; i < 14; ++i) r.y[i] = y[i];
+            r.W3 = W3;
+            r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
+            if (c.goal_mode == 1) {   // goal from the pre-step state, main.py:145-147
+                const T Wv[3] = {y[12], y[13], W3};
+                T Rg[9], b1d[3], Wd[3];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rg[i] = y[3 + i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
+                ensure_so3<T>(Rg);   // get_desired -> state_decomposition
+                traj_wd<T>(Rg, Wv, b1d, Wd);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
+            }
             T act[5];
             bool act_f32 = a.act_f32 != 0;
             if (a.actions) {
@@ -141,124 +358,52 @@ __global__ void __launch_bounds__(QR_BLOCK) k_step(const StepArgs<T> a)
                     for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                 }
             } else {
+                const uint64_t gid = (uint64_t)(a.env_id_offset + e);
                 uint32_t rnd[8];
                 ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len, rnd);
                 if (A == 5) ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len + 1u, rnd + 4);
                 for (int i = 0; i < A; ++i) act[i] = (T)(2.0 * u01(rnd[i]) - 1.0);
                 act_f32 = false;
             }
-            // ---- observation_wrapper: SO(3) check of the incoming R, then integrate ----
-            int st = 0;
-            int fl = ensure_so3<T>(r.y + 3);
-            if (fl & 2) st |= 4;
-            ls.proj += fl & 1;
+            // observation_wrapper: SO(3) check of the incoming R (state_decomposition)
+            int fl = ensure_so3<T>(y + 3);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) r.y[3 + i] = y[3 + i];
             T f, M[3];
             action_to_fM<T>(r, c, act, act_f32, f, M);
-            Dyn<T> d;
-            d.fm = f / r.m; d.g = c.g;
-            d.Mi0 = M[0] / r.J1; d.Mi1 = M[1] / r.J1;
-            d.kw0 = (r.J1 - r.J3) / r.J1; d.kw1 = (r.J3 - r.J1) / r.J1;
-            d.w3dot = M[2] / r.J3;
-            int nf;
+            d.fm = f / p_m; d.g = c.g;
+            d.Mi0 = M[0] / p_J1; d.Mi1 = M[1] / p_J1;
+            d.kw0 = (p_J1 - p_J3) / p_J1; d.kw1 = (p_J3 - p_J1) / p_J1;
+            d.w3dot = M[2] / p_J3;
             bool finite = true;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) finite = finite && (num<T>::abs(r.x[i]) <= num<T>::huge);
+            for (int i = 0; i < 3; ++i) finite = finite && (num<T>::abs(x[i]) <= num<T>::huge);
 #pragma unroll
-            for (int i = 0; i < 14; ++i) finite = finite && (num<T>::abs(r.y[i]) <= num<T>::huge);
-            finite = finite && (num<T>::abs(r.W3) <= num<T>::huge);
+            for (int i = 0; i < 14; ++i) finite = finite && (num<T>::abs(y[i]) <= num<T>::huge);
+            finite = finite && (num<T>::abs(W3) <= num<T>::huge);
             if (!finite) {
-                st |= 1; nf = 0;     // scipy raises ValueError on a non-finite y0; flagged instead
+                // scipy raises ValueError on a non-finite y0; flagged instead, state left as it is
+                ode.t = c.dt; ode.h_abs = 0; ode.rejected = 0; ode.nfev = 0; ode.status = 1; ode.nproj = 0;
+                fin = true;
             } else if (c.integrator == 1 && c.mode == 0) {
                 // explicit Euler (quad.py:252-262), base env only
                 T kk[14];
-                rhs14<T>(r.y, r.W3, d, kk);
+                rhs14<T>(y, W3, d, kk);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) r.x[i] = num<T>::fma(r.y[i], c.dt, r.x[i]);
+                for (int i = 0; i < 3; ++i) x[i] = num<T>::fma(y[i], c.dt, x[i]);
 #pragma unroll
-                for (int i = 0; i < 14; ++i) r.y[i] = num<T>::fma(kk[i], c.dt, r.y[i]);
-                r.W3 = num<T>::fma(d.w3dot, c.dt, r.W3);
-                nf = 1;
+                for (int i = 0; i < 14; ++i) y[i] = num<T>::fma(kk[i], c.dt, y[i]);
+                W3 = num<T>::fma(d.w3dot, c.dt, W3);
+                ode.status = 0; ode.nproj = 0; euler_nfev = 1;
+                fin = true;
             } else {
-                StepResult<T> res = dop853_step<T>(r.x, r.y, r.W3, d, c.dt, c.rtol, c.atol);
-                st |= res.status; nf = res.nfev; ls.proj += res.nproj;
+                dop853_begin<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode);
             }
-            // ---- obs, reward, done ----
-            double rew[2]; int dn[2];
-            if (c.mode == 0) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) o[i] = (float)r.x[i];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) o[3 + i] = (float)r.y[i];
-                o[15] = (float)r.y[12]; o[16] = (float)r.y[13]; o[17] = (float)r.W3;
-                reward_done_quad<T>(r, c, rew, dn);
-            } else {
-                fl = norm_error_state<T>(r, c, o);
-                if (fl & 2) st |= 4;
-                reward_done<T>(c, o, rew, dn);
-            }
-            // ---- episode accounting ----
-            ep_ret[0] += (T)rew[0]; ep_ret[1] += (T)rew[1];
-            ep_len += 1;
-            const bool term = (dn[0] | dn[1]) != 0;
-            const bool trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
-            ls.steps += 1; ls.nfev += nf; ls.rew0 += rew[0]; ls.bad += (st != 0);
-            { int att = (nf - 2) / 12; ls.a1 += att == 1; ls.a2 += att == 2; ls.a3 += att == 3; ls.a4 += att >= 4; }
-            // ---- per-step outputs ----
-            {
-                T* rw = a.reward_roll ? a.reward_roll + ((int64_t)k * N + e) * G : (last ? a.reward + e * G : nullptr);
-                uint8_t* dd = a.done_roll ? a.done_roll + ((int64_t)k * N + e) * G : (last ? a.done + e * G : nullptr);
-                if (rw) { rw[0] = (T)rew[0]; if (G == 2) rw[1] = (T)rew[1]; }
-                if (dd) { dd[0] = (uint8_t)dn[0]; if (G == 2) dd[1] = (uint8_t)dn[1]; }
-                if (a.reward_roll && last) { a.reward[e * G] = (T)rew[0]; if (G == 2) a.reward[e * G + 1] = (T)rew[1]; }
-                if (a.done_roll && last) { a.done[e * G] = (uint8_t)dn[0]; if (G == 2) a.done[e * G + 1] = (uint8_t)dn[1]; }
-                if (last) { a.terminated[e] = (uint8_t)term; a.truncated[e] = (uint8_t)trunc; }
-                if (c.diagnostics && last) a.nfev[e] = nf;
-                if (st) a.status[e] |= (uint8_t)st;
-            }
-            // ---- auto reset (main.py:212-230) ----
-            if (c.autoreset && (term || trunc)) {
-                ls.episodes += 1; ls.length += ep_len; ls.crashed += term; ls.truncated += (trunc && !term);
-                ls.ret0 += (double)ep_ret[0]; ls.ret1 += (double)ep_ret[1]; ls.ret0sq += (double)ep_ret[0] * (double)ep_ret[0];
-                if (last) for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
-                ep_idx += 1;
-                double theta;
-                reset_env<T>(r, ph, gid, ep_idx, c.env_type, c.udm, &theta);
-                if (c.goal_mode == 1) init_goal_mode0<T>(r, theta);
-                store_params_goal(r, a, e, true, c.goal_mode == 1);
-                ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
-                if (c.mode == 0) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) o[i] = (float)r.x[i];
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) o[3 + i] = (float)r.y[i];
-                    o[15] = (float)r.y[12]; o[16] = (float)r.y[13]; o[17] = (float)r.W3;
-                } else {
-                    norm_error_state<T>(r, c, o);   // first obs of the new episode, main.py:230
-                }
-            } else if (c.goal_mode == 1 && last) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = r.goal[9 + i];
-            }
+            if (fl & 2) ode.status |= 4;
+            ode.nproj += fl & 1;
         }
-        // ---- observation tile: registers -> shared (conflict free, O is odd/even-safe) -> full lines ----
-        float* dst = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e0) * O : (last ? a.obs + e0 * O : nullptr);
-        if (dst || (a.obs_roll && last)) {
-            __syncthreads();
-            if (live) for (int i = 0; i < O; ++i) s_tile[tid * O + i] = o[i];
-            __syncthreads();
-            const int64_t rem = a.env_hi - e0;
-            const int nvalid = (int)(rem < QR_BLOCK ? rem : QR_BLOCK) * O;
-            if (dst) for (int i = tid; i < nvalid; i += QR_BLOCK) dst[i] = s_tile[i];
-            if (a.obs_roll && last) { float* d2 = a.obs + e0 * O; for (int i = tid; i < nvalid; i += QR_BLOCK) d2[i] = s_tile[i]; }
-        }
-    }
-
-    if (live) {
-        store_state(r, a, e);
-        a.ep_return[e] = ep_ret[0];
-        if (G == 2) a.ep_return[N + e] = ep_ret[1];
-        a.ep_length[e] = ep_len;
-        a.ep_index[e] = ep_idx;
+        // =============================== phase B ===============================
+        if (busy && !fin) fin = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, lane);
     }
 
     // ---- statistics: warp shuffle reduce -> one shared atomic per warp -> one global atomic per block ----
@@ -266,14 +411,13 @@ __global__ void __launch_bounds__(QR_BLOCK) k_step(const StepArgs<T> a)
         double v[16] = {(double)ls.episodes, ls.ret0, ls.ret1, (double)ls.length, (double)ls.crashed, (double)ls.truncated,
                         ls.ret0sq, (double)ls.steps, (double)ls.bad, (double)ls.nfev, (double)ls.a1, (double)ls.a2,
                         (double)ls.a3, (double)ls.a4, ls.rew0, (double)ls.proj};
-        __syncthreads();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             double s = warp_sum(v[i]);
-            if ((tid & 31) == 0 && s != 0.0) atomicAdd(&s_stats[i], s);
+            if (lane == 0 && s != 0.0) atomicAdd(&s_stats[i], s);
         }
         __syncthreads();
-        if (tid < 16 && s_stats[tid] != 0.0) atomicAdd(&a.stats[tid], s_stats[tid]);
+        if (threadIdx.x < 16 && s_stats[threadIdx.x] != 0.0) atomicAdd(&a.stats[threadIdx.x], s_stats[threadIdx.x]);
     }
 }
 

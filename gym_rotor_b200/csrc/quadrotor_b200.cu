@@ -50,6 +50,7 @@ struct qr_handle {
     void* d_actions; size_t d_actions_bytes;
     double* d_stage; size_t d_stage_bytes;
     cudaStream_t io_stream;
+    int num_sms; int smem_optin; int attr_set[2];
 };
 
 namespace {
@@ -90,8 +91,21 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     a.env_lo = lo; a.env_hi = hi;
     a.actions = actions; a.act_f32 = (act_dtype == QR_F32); a.n_steps = n_steps;
     a.obs_roll = obs_roll; a.reward_roll = (T*)reward_roll; a.done_roll = done_roll;
-    const size_t smem = (size_t)qr::QR_BLOCK * h->O * sizeof(float);
-    qr::k_step<T><<<blocks_for(hi - lo), qr::QR_BLOCK, smem, s>>>(a);
+    // persistent warps: one CTA per SM, as many warps as the stage storage in shared memory allows
+    const size_t per_warp = (size_t)qr::QR_NSLOTS * qr::QR_SLOT_ELEMS * sizeof(T) + 32 * 24 * sizeof(float);
+    int warps = (int)((size_t)h->smem_optin / per_warp);
+    if (warps > qr::QR_MAX_THREADS / 32) warps = qr::QR_MAX_THREADS / 32;
+    if (warps < 1) return fail(QR_ERR_CUDA, "not enough shared memory per block for the step kernel");
+    const int64_t ntiles = (hi - lo + 31) / 32;
+    int64_t grid = (ntiles + warps - 1) / warps;
+    if (grid > h->num_sms) grid = h->num_sms;
+    if (ntiles < (int64_t)warps) warps = (int)ntiles;
+    const size_t smem = per_warp * warps;
+    if (!h->attr_set[sizeof(T) == 8]) {
+        QR_CUDA(cudaFuncSetAttribute(qr::k_step<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->smem_optin / per_warp * per_warp)));
+        h->attr_set[sizeof(T) == 8] = 1;
+    }
+    qr::k_step<T><<<(unsigned)grid, warps * 32, smem, s>>>(a);
     g_launches++;
     QR_CUDA(cudaGetLastError());
     return QR_OK;
@@ -174,6 +188,23 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
         cudaMemset(*al.p, 0, al.bytes);
     }
     QR_CUDA(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
+    QR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    QR_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    h->smem_optin -= 1024;   // static shared memory of the kernel + reserve
+    {
+        static bool tab_done[64] = {false};
+        if (!tab_done[device & 63]) {
+            qr::Tableau t64; qr::TableauF t32;
+            qr::fill_tableau(t64);
+            for (int i = 0; i < 12; ++i) {
+                for (int j = 0; j < 12; ++j) t32.A[i][j] = (float)t64.A[i][j];
+                t32.B[i] = (float)t64.B[i]; t32.E5[i] = (float)t64.E5[i]; t32.E3[i] = (float)t64.E3[i]; t32.C[i] = (float)t64.C[i];
+            }
+            QR_CUDA(cudaMemcpyToSymbol(qr::c_tab64, &t64, sizeof(t64)));
+            QR_CUDA(cudaMemcpyToSymbol(qr::c_tab32, &t32, sizeof(t32)));
+            tab_done[device & 63] = true;
+        }
+    }
     // identity attitude, nominal parameters, b1d = e1: a defined state before the first reset
     {
         std::vector<double> st(18 * n, 0.0), par(6 * n), gl(12 * n, 0.0);
