@@ -20,17 +20,22 @@ template <> struct rn<float> {
     static QR_DEV float add(float a, float b) { return __fadd_rn(a, b); }
     static QR_DEV float sub(float a, float b) { return __fsub_rn(a, b); }
     static QR_DEV float div(float a, float b) { return __fdiv_rn(a, b); }
+    // division by a launch constant: multiply by its host-computed reciprocal (float32 mode is not the
+    // bit-parity mode; the float64 instantiation below keeps numpy's exact quotient)
+    static QR_DEV float divc(float a, float b, float inv_b) { (void)b; return __fmul_rn(a, inv_b); }
 };
 template <> struct rn<double> {
     static QR_DEV double mul(double a, double b) { return __dmul_rn(a, b); }
     static QR_DEV double add(double a, double b) { return __dadd_rn(a, b); }
     static QR_DEV double sub(double a, double b) { return __dsub_rn(a, b); }
     static QR_DEV double div(double a, double b) { return __ddiv_rn(a, b); }
+    static QR_DEV double divc(double a, double b, double inv_b) { (void)inv_b; return __ddiv_rn(a, b); }
 };
 
 // ---- kernel arguments --------------------------------------------------------------------------------
 template <typename T> struct EnvConst {
     T dt, g, rtol, atol, x_lim, v_lim, W_lim, eIx_lim, eIb1_lim, sat, alpha, beta, min_force, euler_lim;
+    T inv_x_lim, inv_v_lim, inv_W_lim, inv_eIx_lim, inv_eIb1_lim;   // host-computed reciprocals (float32 mode only)
     float nCx, nCIx, nCv, nCb1, nCIb1, nCW, nCw12, nCW3;   // negated reward coefficients, as float32 (numpy weak scalars)
     double Cx, Cv, Cb1, CW;                                // base Quad-v0 reward is evaluated in float64
     double rmin, rmin1, rmin2, udm;
@@ -167,7 +172,7 @@ template <typename T> QR_DEV void init_goal_mode0(EnvRegs<T>& e, double theta)
 
 // ---- get_norm_error_state ------------------------------------------------------------------------------------
 // Writes the float32 observation (COUPLED 23, DECOUPLED 15+3) and advances the integral errors once.
-template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<T>& c, float* o)
+template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<T>& c, float* o, const int mode)
 {
     using N = num<T>;
     using A = rn<T>;
@@ -179,9 +184,9 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
     T ex[3], ev[3], eW[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        ex[i] = A::sub(A::div(e.x[i], c.x_lim), A::div(e.goal[i], c.x_lim));
-        ev[i] = A::sub(A::div(e.y[i], c.v_lim), A::div(e.goal[3 + i], c.v_lim));
-        eW[i] = A::sub(A::div(W[i], c.W_lim), A::div(e.goal[9 + i], c.W_lim));
+        ex[i] = A::sub(A::divc(e.x[i], c.x_lim, c.inv_x_lim), A::divc(e.goal[i], c.x_lim, c.inv_x_lim));
+        ev[i] = A::sub(A::divc(e.y[i], c.v_lim, c.inv_v_lim), A::divc(e.goal[3 + i], c.v_lim, c.inv_v_lim));
+        eW[i] = A::sub(A::divc(W[i], c.W_lim, c.inv_W_lim), A::divc(e.goal[9 + i], c.W_lim, c.inv_W_lim));
     }
     const T* b1 = R; const T* b2 = R + 3; const T* b3 = R + 6;
     const T* b1d = e.goal + 6;
@@ -193,24 +198,24 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
     T dn = N::fma(b1c[2], b2[2], N::fma(b1c[1], b2[1], A::mul(b1c[0], b2[0])));
     T dd = N::fma(b1c[2], b1[2], N::fma(b1c[1], b1[1], A::mul(b1c[0], b1[0])));
     const T PI = (T)3.14159265358979323846;
-    T eb1n = A::div(N::atan2(-dn, dd), PI);
+    T eb1n = A::divc(N::atan2(-dn, dd), PI, (T)0.31830988618379067154);
     T eIxn[3], eIb1n;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         T gnew = A::add(A::mul(-c.alpha, e.I[i]), A::mul(ex[i], c.x_lim));
-        e.I[i] = A::add(e.I[i], A::div(A::mul(A::add(e.I[3 + i], gnew), c.dt), (T)2));
+        e.I[i] = A::add(e.I[i], A::mul(A::mul(A::add(e.I[3 + i], gnew), c.dt), (T)0.5));
         e.I[3 + i] = gnew;
-        T q = A::div(e.I[i], c.eIx_lim);
+        T q = A::divc(e.I[i], c.eIx_lim, c.inv_eIx_lim);
         eIxn[i] = q < -c.sat ? -c.sat : (q > c.sat ? c.sat : q);
     }
     {
         T gnew = A::add(A::mul(-c.beta, e.I[6]), A::mul(eb1n, PI));
-        e.I[6] = A::add(e.I[6], A::div(A::mul(A::add(e.I[7], gnew), c.dt), (T)2));
+        e.I[6] = A::add(e.I[6], A::mul(A::mul(A::add(e.I[7], gnew), c.dt), (T)0.5));
         e.I[7] = gnew;
-        T q = A::div(e.I[6], c.eIb1_lim);
+        T q = A::divc(e.I[6], c.eIb1_lim, c.inv_eIb1_lim);
         eIb1n = q < -c.sat ? -c.sat : (q > c.sat ? c.sat : q);
     }
-    if (c.mode == 2) {
+    if (mode == 2) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             o[i] = (float)ex[i]; o[3 + i] = (float)eIxn[i]; o[6 + i] = (float)ev[i]; o[9 + i] = (float)b3[i];
@@ -247,10 +252,10 @@ QR_DEV double interp01(double r, double rmin)
     return __dadd_rn(__dmul_rn(1.0 / (0.0 - rmin), __dsub_rn(r, rmin)), 0.0);
 }
 
-template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float* o, double* rew, int* dn)
+template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float* o, double* rew, int* dn, const int mode)
 {
     dn[0] = 0; dn[1] = 0;
-    if (c.mode == 1) {
+    if (mode == 1) {
         float rx = __fmul_rn(c.nCx, norm2sq_f32(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32(o + 3));
         float rv = __fmul_rn(c.nCv, norm2sq_f32(o + 6)), rw = __fmul_rn(c.nCW, norm2sq_f32(o + 20));
         float a18 = fabsf(o[18]), a19 = fabsf(o[19]);
@@ -324,7 +329,7 @@ template <typename T> QR_DEV void reward_done_quad(const EnvRegs<T>& e, const En
 // a[]: normalised action (already converted to T); act_f32: the caller's array was float32, in which case
 // numpy evaluates the thrust scaling in float32 (python-float * np.float32 -> float32, NEP 50).
 template <typename T>
-QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, bool act_f32, T& f, T* M)
+QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, bool act_f32, T& f, T* M, const int mode)
 {
     using A = rn<T>;
     using N = num<T>;
@@ -332,7 +337,7 @@ QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, 
     const T maxf = A::mul(e.c_tw, hover);                     // quad.py:392
     const T avrg = A::div(A::add(c.min_force, maxf), (T)2);   // quad.py:403
     const T scale = A::sub(maxf, avrg);                       // quad.py:404
-    if (c.mode == 0) {
+    if (mode == 0) {
         T Tm[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -361,7 +366,7 @@ QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, 
         T lo = A::mul((T)4, c.min_force), hi = A::mul((T)4, maxf);
         f = fv < lo ? lo : (fv > hi ? hi : fv);
     }
-    if (c.mode == 1) {
+    if (mode == 1) {
         M[0] = a[1]; M[1] = a[2]; M[2] = a[3];
     } else {
         // decoupled:68-73 on the pre-step (already SO(3)-checked) R and W

@@ -14,7 +14,8 @@
 namespace qr {
 
 constexpr int QR_BLOCK = 128;        // companion kernels (reset, goal init, observation)
-constexpr int QR_MAX_THREADS = 384;  // step kernel: up to 12 persistent warps per SM
+constexpr int QR_MAX_THREADS = 384;  // step kernel: up to 12 persistent warps per SM (float32; 6 warps in float64)
+template <typename T> struct step_threads { static constexpr int value = sizeof(T) == 8 ? 192 : 384; };
 
 template <typename T> struct StepArgs {
     EnvConst<T> c;
@@ -82,9 +83,10 @@ QR_DEV double warp_sum(double v)
 // env.reset -> trajectory_generator.mark_traj_start/get_desired -> set_goal_state -> get_norm_error_state
 // (main.py:226-230).  Works through global memory so that the hot loop's registers are not affected; the
 // caller re-loads the env afterwards.  `o` receives the first observation of the new episode.
-template <typename T>
-__device__ __noinline__ void auto_reset_env(const StepArgs<T>& a, int64_t e, uint32_t episode, float* o)
+template <typename T, int MODE>
+__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* o)
 {
+    const StepArgs<T>& a = *ap;
     const EnvConst<T>& c = a.c;
     const Philox ph{a.key0, a.key1};
     const uint64_t gid = (uint64_t)(a.env_id_offset + e);
@@ -96,14 +98,14 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>& a, int64_t e, uin
 #pragma unroll
         for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * a.n + e];
     }
-    if (c.mode == 0) {
+    if (MODE == 0) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) o[i] = (float)r.x[i];
 #pragma unroll
         for (int i = 0; i < 12; ++i) o[3 + i] = (float)r.y[i];
         o[15] = (float)r.y[12]; o[16] = (float)r.y[13]; o[17] = (float)r.W3;
     } else {
-        norm_error_state<T>(r, c, o);   // first obs of the new episode; advances the integrals once
+        norm_error_state<T>(r, c, o, MODE);   // first obs of the new episode; advances the integrals once
     }
     store_state(r, a, e);
     store_params_goal(r, a, e, true, c.goal_mode == 1);
@@ -126,17 +128,18 @@ struct LocalStats {
 // work of the whole warp.
 //
 // Warp w of the grid owns the 32-env tiles w, w + W, w + 2W, ... (W = warps in the grid); lanes take
-// consecutive envs from that sequence, so loads and stores of a refill are coalesced.
-template <typename T>
-__global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
+// consecutive envs from that sequence, so loads and stores of a refill are coalesced.  Observations go
+// through a per-warp shared tile laid out like the global [32][O] tile, and leave as full 128-byte lines.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid_constant__ StepArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_stats[16];
+    constexpr int O = (MODE == 1) ? 23 : 18;
+    constexpr int A = (MODE == 2) ? 5 : 4;
+    constexpr int G = (MODE == 2) ? 2 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const EnvConst<T>& c = a.c;
-    const int O = (c.mode == 1) ? 23 : 18;
-    const int A = (c.mode == 2) ? 5 : 4;
-    const int G = (c.mode == 2) ? 2 : 1;
     const int64_t N = a.n;
     const size_t per_warp = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T) + 32 * 24 * sizeof(float);
     T* ks = reinterpret_cast<T*>(smem_raw + warp * per_warp);
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
     Dyn<T> d;
     OdeLane<T> ode;
     T ep_ret[2] = {0, 0};
-    int ep_len = 0, euler_nfev = 0;
+    int ep_len = 0;
     uint32_t ep_idx = 0;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -180,12 +183,12 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
         // ---- A1: finish the env.step that just completed ----
         const unsigned finmask = __ballot_sync(0xffffffffu, fin);
         if (finmask) {
-            const bool last = (k == a.n_steps - 1);
+            float o[23];
             bool did_reset = false;
+            const bool last = (k == a.n_steps - 1);
             if (fin) {
-                float o[23];
                 int st = ode.status;
-                const int nf = (c.integrator == 1 && c.mode == 0) ? euler_nfev : ode.nfev;
+                const int nf = ode.nfev;
                 ls.proj += ode.nproj;
                 EnvRegs<T> r;
 #pragma unroll
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
 #pragma unroll
                 for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * N + e];
                 double rew[2]; int dn[2];
-                if (c.mode == 0) {
+                if (MODE == 0) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) o[i] = (float)x[i];
 #pragma unroll
@@ -206,13 +209,14 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
                     o[15] = (float)y[12]; o[16] = (float)y[13]; o[17] = (float)W3;
                     reward_done_quad<T>(r, c, rew, dn);
                 } else {
-                    int fl = norm_error_state<T>(r, c, o);
+                    int fl = norm_error_state<T>(r, c, o, MODE);
                     if (fl & 2) st |= 4;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) I[i] = r.I[i];
-                    reward_done<T>(c, o, rew, dn);
+                    reward_done<T>(c, o, rew, dn, MODE);
                 }
-                ep_ret[0] += (T)rew[0]; ep_ret[1] += (T)rew[1];
+                ep_ret[0] += (T)rew[0];
+                if (G == 2) ep_ret[1] += (T)rew[1];
                 ep_len += 1;
                 const bool term = (dn[0] | dn[1]) != 0;
                 const bool trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
@@ -231,36 +235,51 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
                 if (c.autoreset && (term || trunc)) {
                     ls.episodes += 1; ls.length += ep_len; ls.crashed += term; ls.truncated += (trunc && !term);
                     ls.ret0 += (double)ep_ret[0]; ls.ret1 += (double)ep_ret[1]; ls.ret0sq += (double)ep_ret[0] * (double)ep_ret[0];
-                    if (last) for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
+                    if (last) {
+#pragma unroll
+                        for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
+                    }
                     ep_idx += 1;
-                    auto_reset_env<T>(a, e, ep_idx, o);
+                    float o2[23];
+                    auto_reset_env<T, MODE>(&a, e, ep_idx, o2);
+#pragma unroll
+                    for (int i = 0; i < O; ++i) o[i] = o2[i];
                     ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
                     did_reset = true;
                 }
-                for (int i = 0; i < O; ++i) os[lane * O + i] = o[i];
             }
-            // ---- observation rows: shared -> global, one 4*O-byte row per finished lane, written by O lanes ----
-            __syncwarp();
-            {
-                float* dst = a.obs_roll ? a.obs_roll + (int64_t)k * N * O : (last ? a.obs : nullptr);
-                // `k` and `last` are per lane; rows are copied with the owner's values broadcast by shuffle
-                unsigned m = finmask;
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int64_t es = __shfl_sync(0xffffffffu, e, src);
-                    const int kk = __shfl_sync(0xffffffffu, k, src);
-                    const bool lst = (kk == a.n_steps - 1);
-                    float* drow = a.obs_roll ? a.obs_roll + ((int64_t)kk * N + es) * O : (lst ? a.obs + es * O : nullptr);
-                    if (lane < O) {
-                        const float v = os[src * O + lane];
-                        if (drow) drow[lane] = v;
-                        if (a.obs_roll && lst) a.obs[es * O + lane] = v;
+            // ---- observation rows: registers -> shared tile (row = env & 31) -> global, 128-byte lines.
+            // Finished lanes usually belong to one 32-env tile and one sub-step; stragglers (lanes that needed
+            // another attempt) belong to an older tile and are flushed in a further round of this loop.
+            unsigned rem = finmask;
+            while (rem) {
+                const int lead = __ffs(rem) - 1;
+                const int64_t tb = __shfl_sync(0xffffffffu, e & ~(int64_t)31, lead);
+                const int kk = __shfl_sync(0xffffffffu, k, lead);
+                const bool mine = fin && ((e & ~(int64_t)31) == tb) && (k == kk);
+                const unsigned grp = __ballot_sync(0xffffffffu, mine);
+                const unsigned rows = __reduce_or_sync(0xffffffffu, mine ? (1u << (int)(e & 31)) : 0u);
+                rem &= ~grp;
+                if (mine) {
+                    float* row = os + (int)(e & 31) * O;
+#pragma unroll
+                    for (int i = 0; i < O; ++i) row[i] = o[i];
+                }
+                __syncwarp();
+                const bool lst = (kk == a.n_steps - 1);
+                float* d1 = a.obs_roll ? a.obs_roll + ((int64_t)kk * N + tb) * O : (lst ? a.obs + tb * O : nullptr);
+                float* d2 = (a.obs_roll && lst) ? a.obs + tb * O : nullptr;
+#pragma unroll 1
+                for (int q = lane; q < 32 * O; q += 32) {
+                    const int r_ = q / O;
+                    if ((rows >> r_) & 1u) {
+                        const float v = os[q];
+                        if (d1) d1[q] = v;
+                        if (d2) d2[q] = v;
                     }
                 }
-                (void)dst;
+                __syncwarp();
             }
-            __syncwarp();
             if (fin) {
                 fin = false;
                 if (did_reset) {
@@ -330,8 +349,6 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
             EnvRegs<T> r;
 #pragma unroll
             for (int i = 0; i < 3; ++i) r.x[i] = x[i];
-#pragma unroll
-            for (int i = 0; i < 14; ++i) r.y[i] = y[i];
             r.W3 = W3;
             r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
             if (c.goal_mode == 1) {   // goal from the pre-step state, main.py:145-147
@@ -352,9 +369,16 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
                 const int64_t base = ((int64_t)k * N + e) * A;
                 if (a.act_f32) {
                     const float* p = (const float*)a.actions + base;
-                    for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
+                    if (A == 4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+                        act[0] = (T)v.x; act[1] = (T)v.y; act[2] = (T)v.z; act[3] = (T)v.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
+                    }
                 } else {
                     const double* p = (const double*)a.actions + base;
+#pragma unroll
                     for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                 }
             } else {
@@ -362,15 +386,16 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
                 uint32_t rnd[8];
                 ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len, rnd);
                 if (A == 5) ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len + 1u, rnd + 4);
+#pragma unroll
                 for (int i = 0; i < A; ++i) act[i] = (T)(2.0 * u01(rnd[i]) - 1.0);
                 act_f32 = false;
             }
             // observation_wrapper: SO(3) check of the incoming R (state_decomposition)
             int fl = ensure_so3<T>(y + 3);
 #pragma unroll
-            for (int i = 0; i < 9; ++i) r.y[3 + i] = y[3 + i];
+            for (int i = 0; i < 14; ++i) r.y[i] = y[i];
             T f, M[3];
-            action_to_fM<T>(r, c, act, act_f32, f, M);
+            action_to_fM<T>(r, c, act, act_f32, f, M, MODE);
             d.fm = f / p_m; d.g = c.g;
             d.Mi0 = M[0] / p_J1; d.Mi1 = M[1] / p_J1;
             d.kw0 = (p_J1 - p_J3) / p_J1; d.kw1 = (p_J3 - p_J1) / p_J1;
@@ -385,7 +410,7 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
                 // scipy raises ValueError on a non-finite y0; flagged instead, state left as it is
                 ode.t = c.dt; ode.h_abs = 0; ode.rejected = 0; ode.nfev = 0; ode.status = 1; ode.nproj = 0;
                 fin = true;
-            } else if (c.integrator == 1 && c.mode == 0) {
+            } else if (MODE == 0 && c.integrator == 1) {
                 // explicit Euler (quad.py:252-262), base env only
                 T kk[14];
                 rhs14<T>(y, W3, d, kk);
@@ -394,7 +419,7 @@ __global__ void __launch_bounds__(QR_MAX_THREADS, 1) k_step(const StepArgs<T> a)
 #pragma unroll
                 for (int i = 0; i < 14; ++i) y[i] = num<T>::fma(kk[i], c.dt, y[i]);
                 W3 = num<T>::fma(d.w3dot, c.dt, W3);
-                ode.status = 0; ode.nproj = 0; euler_nfev = 1;
+                ode.status = 0; ode.nproj = 0; ode.nfev = 1;
                 fin = true;
             } else {
                 dop853_begin<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode);
@@ -477,7 +502,7 @@ __global__ void __launch_bounds__(QR_BLOCK) k_norm_error_state(const StepArgs<T>
         for (int i = 0; i < 12; ++i) o[3 + i] = (float)r.y[i];
         o[15] = (float)r.y[12]; o[16] = (float)r.y[13]; o[17] = (float)r.W3;
     } else {
-        int fl = norm_error_state<T>(r, a.c, o);
+        int fl = norm_error_state<T>(r, a.c, o, a.c.mode);
         if (fl & 2) a.status[e] |= 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) a.integ[i * a.n + e] = r.I[i];

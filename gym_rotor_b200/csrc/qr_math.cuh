@@ -25,9 +25,11 @@ template <> struct num<float> {
     static QR_DEV float nextafter(float a, float b) { return nextafterf(a, b); }
     static QR_DEV float inf() { return __int_as_float(0x7f800000); }
     // x^(1/8) and x^(-1/8) by square-root chains: <= 2 ulp, no transcendental (only scales the step size)
-    static QR_DEV float root8(float x) { return sqrtf(sqrtf(sqrtf(x))); }
-    static QR_DEV float inv_root8(float x) { return rsqrtf(sqrtf(sqrtf(x))); }
-    static QR_DEV float recip(float x) { return 1.0f / x; }
+    static QR_DEV float asqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    static QR_DEV float root8(float x) { return asqrt(asqrt(asqrt(x))); }
+    static QR_DEV float inv_root8(float x) { return rsqrtf(asqrt(asqrt(x))); }
+    // reciprocal of an error scale (feeds norms that only steer the step size): MUFU.RCP, <= 1 ulp
+    static QR_DEV float recip(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
     static constexpr float eps_jacobi = 1e-7f;
     static constexpr float huge = 3.0e38f;
 };

@@ -64,6 +64,8 @@ template <typename T> qr::StepArgs<T> make_args(const qr_handle* h)
     a.c.x_lim = (T)c.x_lim; a.c.v_lim = (T)c.v_lim; a.c.W_lim = (T)c.W_lim;
     a.c.eIx_lim = (T)c.eIx_lim; a.c.eIb1_lim = (T)c.eIb1_lim; a.c.sat = (T)c.sat_sigma;
     a.c.alpha = (T)c.alpha; a.c.beta = (T)c.beta; a.c.min_force = (T)c.min_force; a.c.euler_lim = (T)c.euler_lim_deg;
+    a.c.inv_x_lim = (T)(1.0 / c.x_lim); a.c.inv_v_lim = (T)(1.0 / c.v_lim); a.c.inv_W_lim = (T)(1.0 / c.W_lim);
+    a.c.inv_eIx_lim = (T)(1.0 / c.eIx_lim); a.c.inv_eIb1_lim = (T)(1.0 / c.eIb1_lim);
     a.c.nCx = (float)(-c.Cx); a.c.nCIx = (float)(-c.CIx); a.c.nCv = (float)(-c.Cv); a.c.nCb1 = (float)(-c.Cb1);
     a.c.nCIb1 = (float)(-c.CIb1); a.c.nCW = (float)(-c.CW); a.c.nCw12 = (float)(-c.Cw12); a.c.nCW3 = (float)(-c.CW3);
     a.c.Cx = c.Cx; a.c.Cv = c.Cv; a.c.Cb1 = c.Cb1; a.c.CW = c.CW;
@@ -94,18 +96,20 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     // persistent warps: one CTA per SM, as many warps as the stage storage in shared memory allows
     const size_t per_warp = (size_t)qr::QR_NSLOTS * qr::QR_SLOT_ELEMS * sizeof(T) + 32 * 24 * sizeof(float);
     int warps = (int)((size_t)h->smem_optin / per_warp);
-    if (warps > qr::QR_MAX_THREADS / 32) warps = qr::QR_MAX_THREADS / 32;
+    if (warps > qr::step_threads<T>::value / 32) warps = qr::step_threads<T>::value / 32;
     if (warps < 1) return fail(QR_ERR_CUDA, "not enough shared memory per block for the step kernel");
     const int64_t ntiles = (hi - lo + 31) / 32;
     int64_t grid = (ntiles + warps - 1) / warps;
     if (grid > h->num_sms) grid = h->num_sms;
     if (ntiles < (int64_t)warps) warps = (int)ntiles;
     const size_t smem = per_warp * warps;
+    void (*kern)(const qr::StepArgs<T>) = (h->cfg.mode == QR_MODE_COUPLED) ? qr::k_step<T, 1>
+                                          : (h->cfg.mode == QR_MODE_DECOUPLED) ? qr::k_step<T, 2> : qr::k_step<T, 0>;
     if (!h->attr_set[sizeof(T) == 8]) {
-        QR_CUDA(cudaFuncSetAttribute(qr::k_step<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->smem_optin / per_warp * per_warp)));
+        QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->smem_optin / per_warp * per_warp)));
         h->attr_set[sizeof(T) == 8] = 1;
     }
-    qr::k_step<T><<<(unsigned)grid, warps * 32, smem, s>>>(a);
+    kern<<<(unsigned)grid, warps * 32, smem, s>>>(a);
     g_launches++;
     QR_CUDA(cudaGetLastError());
     return QR_OK;
