@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libquadrotor_b200.so")
+LIB_PATH = os.environ.get("QR_LIB_PATH") or os.path.join(HERE, "csrc", "libquadrotor_b200.so")  # override: A/B kernel variants
 
 QR_OK = 0
 MODE_QUAD, MODE_COUPLED, MODE_DECOUPLED = 0, 1, 2

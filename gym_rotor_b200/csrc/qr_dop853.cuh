@@ -28,6 +28,10 @@
 #include "qr_math.cuh"
 #include "dop853_tableau.h"
 
+#ifndef QR_OPT_PAIR2
+#define QR_OPT_PAIR2 0
+#endif
+
 namespace qr {
 
 // ---- tableau in constant memory (uniform-indexed loads in the rolled stage loop) ------------------------
@@ -91,37 +95,38 @@ QR_DEV int k_slot(int j) { return j < 5 ? ((j + 1) & 1) : j - 3; }   // K1,K3 ->
 template <typename T> struct vec4 { T a, b, c, d; };
 template <typename T> struct vec2 { T a, b; };
 
-template <typename T> QR_DEV void ks_load(const T* slot, int lane, T* k)
+// `col` = slot base + lane * 4 elements.  float: groups g=0..2 at col + g*128 (16 B each), tail at
+// slot + 384 + lane*2 = col + 384 - lane*2.  double: 7 groups of 2 at slot + (g*32 + lane)*2 = col + g*64 - lane*2.
+template <typename T> QR_DEV void ks_load_lane(const T* col, int lane, T* k)
 {
     if (sizeof(T) == 4) {
-        const float4* p = reinterpret_cast<const float4*>(slot);
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-            float4 v = p[g * 32 + lane];
+            float4 v = *reinterpret_cast<const float4*>(col + g * 128);
             k[4 * g] = (T)v.x; k[4 * g + 1] = (T)v.y; k[4 * g + 2] = (T)v.z; k[4 * g + 3] = (T)v.w;
         }
-        float2 w = reinterpret_cast<const float2*>(slot + 384)[lane];
+        float2 w = *reinterpret_cast<const float2*>(col + 384 - lane * 2);
         k[12] = (T)w.x; k[13] = (T)w.y;
     } else {
-        const double2* p = reinterpret_cast<const double2*>(slot);
+        const T* p = col - lane * 2;
 #pragma unroll
         for (int g = 0; g < 7; ++g) {
-            double2 v = p[g * 32 + lane];
+            double2 v = *reinterpret_cast<const double2*>(p + g * 64);
             k[2 * g] = (T)v.x; k[2 * g + 1] = (T)v.y;
         }
     }
 }
-template <typename T> QR_DEV void ks_store(T* slot, int lane, const T* k)
+template <typename T> QR_DEV void ks_store_lane(T* col, int lane, const T* k)
 {
     if (sizeof(T) == 4) {
-        float4* p = reinterpret_cast<float4*>(slot);
 #pragma unroll
-        for (int g = 0; g < 3; ++g) p[g * 32 + lane] = make_float4((float)k[4 * g], (float)k[4 * g + 1], (float)k[4 * g + 2], (float)k[4 * g + 3]);
-        reinterpret_cast<float2*>(slot + 384)[lane] = make_float2((float)k[12], (float)k[13]);
+        for (int g = 0; g < 3; ++g)
+            *reinterpret_cast<float4*>(col + g * 128) = make_float4((float)k[4 * g], (float)k[4 * g + 1], (float)k[4 * g + 2], (float)k[4 * g + 3]);
+        *reinterpret_cast<float2*>(col + 384 - lane * 2) = make_float2((float)k[12], (float)k[13]);
     } else {
-        double2* p = reinterpret_cast<double2*>(slot);
+        T* p = col - lane * 2;
 #pragma unroll
-        for (int g = 0; g < 7; ++g) p[g * 32 + lane] = make_double2((double)k[2 * g], (double)k[2 * g + 1]);
+        for (int g = 0; g < 7; ++g) *reinterpret_cast<double2*>(p + g * 64) = make_double2((double)k[2 * g], (double)k[2 * g + 1]);
     }
 }
 
@@ -237,46 +242,64 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
 // accept / reject and step-size update.  Returns true when the lane is finished with the whole interval
 // (t reached Tend, or the integrator gave up and keeps the last accepted state).
 // ks: this warp's stage storage, lane: lane id.
+//
+// The function is executed by ALL lanes of the warp (control flow stays warp-uniform, so loop counters and
+// tableau loads live in the uniform datapath); `live` says whether this lane really has an attempt to make.
+// Lanes without one run on whatever benign state they hold and commit nothing.
 template <typename T>
 QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, const T rtol, const T atol, T* K0,
-                           OdeLane<T>& o, T* ks, const int lane)
+                           OdeLane<T>& o, T* ks, const int lane, const bool live)
 {
     using N = num<T>;
     using TB = tab<T>;
     const T min_step = (T)10 * N::abs(N::nextafter(o.t, N::inf()) - o.t);
-    if (o.h_abs < min_step) { o.status |= 2; return true; }   // TOO_SMALL_STEP: keep the last accepted y
+    const bool too_small = o.h_abs < min_step;   // TOO_SMALL_STEP: keep the last accepted y
     T t_new = o.t + o.h_abs;
     if (t_new - Tend > (T)0) t_new = Tend;
     const T h = t_new - o.t;
-    o.h_abs = N::abs(h);
-    o.nfev += 12;
 
     // running sums for x (x' = v): B, E5 and E3 weighted stage velocities
     T xb[3], x5[3], x3[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) { xb[i] = TB::B(0) * y[i]; x5[i] = TB::E5(0) * y[i]; x3[i] = TB::E3(0) * y[i]; }
+    int nproj = 0, bad = 0;
+    T* const kl = ks + lane * 4;   // this lane's column inside every slot (see ks_load / ks_store)
 
 #pragma unroll 1
     for (int s = 1; s <= 11; ++s) {
-        T acc[14];
-        const T a0 = TB::A(s, 0);
-#pragma unroll
-        for (int i = 0; i < 14; ++i) acc[i] = a0 * K0[i];
-        const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
-#pragma unroll 1
-        for (int j = jlo; j < s; ++j) {
-            const T c = TB::A(s, j);
-            T k[14];
-            ks_load<T>(ks + k_slot(j) * QR_SLOT_ELEMS, lane, k);
-#pragma unroll
-            for (int i = 0; i < 14; ++i) acc[i] = N::fma(c, k[i], acc[i]);
-        }
+        // ys = y + sum_j (h a_sj) K_j
         T ys[14];
-#pragma unroll
-        for (int i = 0; i < 14; ++i) ys[i] = N::fma(h, acc[i], y[i]);
-        const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
         {
-            const T bs = TB::B(s), e5s = TB::E5(s), e3s = TB::E3(s);   // zero for s < 5
+            const T ha0 = h * TB::A(s, 0);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) ys[i] = N::fma(ha0, K0[i], y[i]);
+        }
+        const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
+        int j = jlo;
+#if QR_OPT_PAIR2
+#pragma unroll 1
+        for (; j + 1 < s; j += 2) {   // two K vectors in flight per trip
+            const T c0 = h * TB::A(s, j), c1 = h * TB::A(s, j + 1);
+            T k0[14], k1[14];
+            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k0);
+            ks_load_lane<T>(kl + k_slot(j + 1) * QR_SLOT_ELEMS, lane, k1);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) ys[i] = N::fma(c1, k1[i], N::fma(c0, k0[i], ys[i]));
+        }
+        if (j < s) {
+#else
+#pragma unroll 1
+        for (; j < s; ++j) {
+#endif
+            const T c = h * TB::A(s, j);
+            T k[14];
+            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) ys[i] = N::fma(c, k[i], ys[i]);
+        }
+        const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
+        if (s >= 5) {
+            const T bs = TB::B(s), e5s = TB::E5(s), e3s = TB::E3(s);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 xb[i] = N::fma(bs, ys[i], xb[i]); x5[i] = N::fma(e5s, ys[i], x5[i]); x3[i] = N::fma(e3s, ys[i], x3[i]);
@@ -284,8 +307,8 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         }
         T kn[14];
         int fl = rhs14<T>(ys, W3s, d, kn);
-        o.nproj += fl & 1; if (fl & 2) o.status |= 4;
-        ks_store<T>(ks + k_slot(s) * QR_SLOT_ELEMS, lane, kn);
+        nproj += fl & 1; bad |= fl & 2;
+        ks_store_lane<T>(kl + k_slot(s) * QR_SLOT_ELEMS, lane, kn);
     }
 
     // y_new = y + h * sum_s B_s K_s ; error estimates (rk.py:683-691)
@@ -299,7 +322,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     for (int j = 5; j <= 11; ++j) {
         const T bj = TB::B(j), e5j = TB::E5(j), e3j = TB::E3(j);
         T k[14];
-        ks_load<T>(ks + k_slot(j) * QR_SLOT_ELEMS, lane, k);
+        ks_load_lane<T>(kl + (j - 3) * QR_SLOT_ELEMS, lane, k);
 #pragma unroll
         for (int i = 0; i < 14; ++i) { sb[i] = N::fma(bj, k[i], sb[i]); s5[i] = N::fma(e5j, k[i], s5[i]); s3[i] = N::fma(e3j, k[i], s3[i]); }
     }
@@ -323,6 +346,11 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     if (e5n == (T)0 && e3n == (T)0) err = 0;
     else err = N::abs(h) * e5n * N::rsqrt((e5n + (T)0.01 * e3n) * (T)18);
 
+    if (!live) return false;
+    if (too_small) { o.status |= 2; return true; }
+    o.h_abs = N::abs(h);
+    o.nfev += 12;
+    o.nproj += nproj; if (bad) o.status |= 4;
     if (err < (T)1) {   // accept
 #pragma unroll
         for (int i = 0; i < 3; ++i) x[i] = xnew[i];

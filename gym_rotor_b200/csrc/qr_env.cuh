@@ -38,7 +38,7 @@ template <typename T> struct EnvConst {
     T inv_x_lim, inv_v_lim, inv_W_lim, inv_eIx_lim, inv_eIb1_lim;   // host-computed reciprocals (float32 mode only)
     float nCx, nCIx, nCv, nCb1, nCIb1, nCW, nCw12, nCW3;   // negated reward coefficients, as float32 (numpy weak scalars)
     double Cx, Cv, Cb1, CW;                                // base Quad-v0 reward is evaluated in float64
-    double rmin, rmin1, rmin2, udm;
+    double rmin, rmin1, rmin2, slope, slope1, slope2, udm;
     int mode, integrator, autoreset, goal_mode, env_type, max_episode_steps, diagnostics;
 };
 
@@ -243,13 +243,13 @@ QR_DEV float norm2sq_f32(const float* v)
     float n = __fsqrt_rn((float)s);
     return __fmul_rn(n, n);
 }
-QR_DEV double interp01(double r, double rmin)
+QR_DEV double interp01(double r, double rmin, double slope)
 {
-    // np.interp(r, [rmin, 0], [0, 1])
+    // np.interp(r, [rmin, 0], [0, 1]); slope = 1 / (0 - rmin), computed once on the host
     if (r != r) return r;
     if (r <= rmin) return 0.0;
     if (r >= 0.0) return 1.0;
-    return __dadd_rn(__dmul_rn(1.0 / (0.0 - rmin), __dsub_rn(r, rmin)), 0.0);
+    return __dadd_rn(__dmul_rn(slope, __dsub_rn(r, rmin)), 0.0);
 }
 
 template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float* o, double* rew, int* dn, const int mode)
@@ -264,7 +264,7 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
 #pragma unroll
         for (int i = 0; i < 3; ++i)
             if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[20 + i]) >= 1.0f) dn[0] = 1;
-        rew[0] = dn[0] ? -1.0 : interp01((double)r, c.rmin);
+        rew[0] = dn[0] ? -1.0 : interp01((double)r, c.rmin, c.slope);
         rew[1] = 0.0;
     } else {
         float rx = __fmul_rn(c.nCx, norm2sq_f32(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32(o + 3));
@@ -277,8 +277,8 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
         for (int i = 0; i < 3; ++i)
             if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[12 + i]) >= 1.0f) dn[0] = 1;
         if (a2 >= 1.0f) dn[1] = 1;
-        rew[0] = dn[0] ? -1.0 : interp01((double)r1, c.rmin1);
-        rew[1] = dn[1] ? -1.0 : interp01((double)r2, c.rmin2);
+        rew[0] = dn[0] ? -1.0 : interp01((double)r1, c.rmin1, c.slope1);
+        rew[1] = dn[1] ? -1.0 : interp01((double)r2, c.rmin2, c.slope2);
     }
 }
 
@@ -321,7 +321,7 @@ template <typename T> QR_DEV void reward_done_quad(const EnvRegs<T>& e, const En
     }
     if (fabs(roll) >= (double)c.euler_lim || fabs(pitch) >= (double)c.euler_lim) d = 1;
     dn[0] = d; dn[1] = 0;
-    rew[0] = d ? -1.0 : interp01(r, c.rmin);
+    rew[0] = d ? -1.0 : interp01(r, c.rmin, c.slope);
     rew[1] = 0.0;
 }
 
@@ -333,9 +333,9 @@ QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, 
 {
     using A = rn<T>;
     using N = num<T>;
-    const T hover = A::div(A::mul(e.m, c.g), (T)4);           // quad.py:390
+    const T hover = A::mul(A::mul(e.m, c.g), (T)0.25);        // quad.py:390  (x/4 == x*0.25 exactly)
     const T maxf = A::mul(e.c_tw, hover);                     // quad.py:392
-    const T avrg = A::div(A::add(c.min_force, maxf), (T)2);   // quad.py:403
+    const T avrg = A::mul(A::add(c.min_force, maxf), (T)0.5); // quad.py:403  (x/2 == x*0.5 exactly)
     const T scale = A::sub(maxf, avrg);                       // quad.py:404
     if (mode == 0) {
         T Tm[4];

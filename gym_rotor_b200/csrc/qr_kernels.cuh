@@ -11,11 +11,18 @@
 #pragma once
 #include "qr_env.cuh"
 
+#ifndef QR_OPT_PREFETCH
+#define QR_OPT_PREFETCH 0
+#endif
+
 namespace qr {
 
 constexpr int QR_BLOCK = 128;        // companion kernels (reset, goal init, observation)
 constexpr int QR_MAX_THREADS = 384;  // step kernel: up to 12 persistent warps per SM (float32; 6 warps in float64)
-template <typename T> struct step_threads { static constexpr int value = sizeof(T) == 8 ? 192 : 384; };
+#ifndef QR_STEP_THREADS_F32
+#define QR_STEP_THREADS_F32 384
+#endif
+template <typename T> struct step_threads { static constexpr int value = sizeof(T) == 8 ? 192 : QR_STEP_THREADS_F32; };
 
 template <typename T> struct StepArgs {
     EnvConst<T> c;
@@ -72,6 +79,8 @@ template <typename T> QR_DEV void store_params_goal(const EnvRegs<T>& r, const S
     }
 }
 
+QR_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 QR_DEV double warp_sum(double v)
 {
 #pragma unroll
@@ -84,9 +93,11 @@ QR_DEV double warp_sum(double v)
 // (main.py:226-230).  Works through global memory so that the hot loop's registers are not affected; the
 // caller re-loads the env afterwards.  `o` receives the first observation of the new episode.
 template <typename T, int MODE>
-__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* o)
+__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* dst1, float* dst2)
 {
     const StepArgs<T>& a = *ap;
+    constexpr int O = (MODE == 1) ? 23 : 18;
+    float o[23];
     const EnvConst<T>& c = a.c;
     const Philox ph{a.key0, a.key1};
     const uint64_t gid = (uint64_t)(a.env_id_offset + e);
@@ -109,12 +120,19 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
     }
     store_state(r, a, e);
     store_params_goal(r, a, e, true, c.goal_mode == 1);
+#pragma unroll
+    for (int i = 0; i < O; ++i) {
+        if (dst1) dst1[i] = o[i];
+        if (dst2) dst2[i] = o[i];
+    }
 }
 
-struct LocalStats {
-    double ret0, ret1, ret0sq, rew0;
-    int episodes, length, crashed, truncated, steps, bad, nfev, a1, a2, a3, a4, proj;
-};
+QR_DEV float warp_sum_f(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 // ---- the step kernel ---------------------------------------------------------------------------------------
 // Persistent warps.  Every lane runs the state machine
@@ -129,25 +147,40 @@ struct LocalStats {
 //
 // Warp w of the grid owns the 32-env tiles w, w + W, w + 2W, ... (W = warps in the grid); lanes take
 // consecutive envs from that sequence, so loads and stores of a refill are coalesced.  Observations go
-// through a per-warp shared tile laid out like the global [32][O] tile, and leave as full 128-byte lines.
+// through a per-warp shared tile and leave as full 128-byte lines.  Episode statistics are reduced with
+// warp votes / REDUX into per-warp shared accumulators (no per-lane counters: registers are the scarce
+// resource at 12 warps per SM) and flushed with one atomic per statistic and warp at the end.
+//
+// Per-warp shared memory: KS[9][14][32] T (stage derivatives) | OS[32][O] f32 (observation rows, by lane) |
+//                         WS[16] f64 (statistics) | ROWMAP[32] u8 (tile row -> lane)
+template <typename T> struct warp_smem {
+    static constexpr size_t ks_bytes = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T);
+    static constexpr size_t os_bytes = 32 * 23 * sizeof(float);
+    static constexpr size_t ws_bytes = 16 * sizeof(double);
+    static constexpr size_t map_bytes = 32;
+    static constexpr size_t bytes = ks_bytes + os_bytes + ws_bytes + map_bytes;   // multiple of 16
+};
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid_constant__ StepArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double s_stats[16];
     constexpr int O = (MODE == 1) ? 23 : 18;
     constexpr int A = (MODE == 2) ? 5 : 4;
     constexpr int G = (MODE == 2) ? 2 : 1;
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const EnvConst<T>& c = a.c;
     const int64_t N = a.n;
-    const size_t per_warp = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T) + 32 * 24 * sizeof(float);
-    T* ks = reinterpret_cast<T*>(smem_raw + warp * per_warp);
-    float* os = reinterpret_cast<float*>(smem_raw + warp * per_warp + (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T));
+    unsigned char* wbase = smem_raw + warp * warp_smem<T>::bytes;
+    T* ks = reinterpret_cast<T*>(wbase);
+    float* os = reinterpret_cast<float*>(wbase + warp_smem<T>::ks_bytes);
+    double* ws = reinterpret_cast<double*>(wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes);
+    unsigned char* rowmap = wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes + warp_smem<T>::ws_bytes;
     const Philox ph{a.key0, a.key1};
 
-    if (threadIdx.x < 16) s_stats[threadIdx.x] = 0.0;
-    __syncthreads();
+    if (lane < 16) ws[lane] = 0.0;
+    __syncwarp();
 
     // this warp's virtual env sequence
     const int64_t gw = (int64_t)blockIdx.x * wpb + warp, W = (int64_t)gridDim.x * wpb;
@@ -168,28 +201,29 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     T ep_ret[2] = {0, 0};
     int ep_len = 0;
     uint32_t ep_idx = 0;
-    LocalStats ls = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = 0;
 #pragma unroll
     for (int i = 0; i < 14; ++i) { y[i] = 0; K0[i] = 0; }
+    y[3] = 1; y[7] = 1; y[11] = 1;   // idle lanes run the (warp-uniform) attempt on a benign state: R = I
 #pragma unroll
     for (int i = 0; i < 8; ++i) I[i] = 0;
     d.fm = d.g = d.Mi0 = d.Mi1 = d.kw0 = d.kw1 = d.w3dot = 0;
-    ode.t = 0; ode.h_abs = 0; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0;
+    ode.t = 0; ode.h_abs = c.dt; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0;
 
     for (;;) {
         // =============================== phase A ===============================
         // ---- A1: finish the env.step that just completed ----
-        const unsigned finmask = __ballot_sync(0xffffffffu, fin);
+        const unsigned finmask = __ballot_sync(FULL, fin);
         if (finmask) {
-            float o[23];
-            bool did_reset = false;
+            bool did_reset = false, term = false, trunc = false;
+            int nf = 0, st = 0, nproj = 0, ep_len_done = 0;
+            float rew0f = 0.f;
+            T ret_done0 = 0, ret_done1 = 0;
             const bool last = (k == a.n_steps - 1);
             if (fin) {
-                int st = ode.status;
-                const int nf = ode.nfev;
-                ls.proj += ode.nproj;
+                float o[23];
+                st = ode.status; nf = ode.nfev; nproj = ode.nproj;
                 EnvRegs<T> r;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) r.x[i] = x[i];
@@ -215,13 +249,15 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < 8; ++i) I[i] = r.I[i];
                     reward_done<T>(c, o, rew, dn, MODE);
                 }
+                // the observation row leaves the registers at once (tile row = lane; see the copy below)
+#pragma unroll
+                for (int i = 0; i < O; ++i) os[lane * O + i] = o[i];
+                rew0f = (float)rew[0];
                 ep_ret[0] += (T)rew[0];
                 if (G == 2) ep_ret[1] += (T)rew[1];
                 ep_len += 1;
-                const bool term = (dn[0] | dn[1]) != 0;
-                const bool trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
-                ls.steps += 1; ls.nfev += nf; ls.rew0 += rew[0]; ls.bad += (st != 0);
-                { int att = (nf - 2) / 12; ls.a1 += att == 1; ls.a2 += att == 2; ls.a3 += att == 3; ls.a4 += att >= 4; }
+                term = (dn[0] | dn[1]) != 0;
+                trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
                 // per-step scalar outputs
                 T* rw = a.reward_roll ? a.reward_roll + ((int64_t)k * N + e) * G : (last ? a.reward + e * G : nullptr);
                 uint8_t* dd = a.done_roll ? a.done_roll + ((int64_t)k * N + e) * G : (last ? a.done + e * G : nullptr);
@@ -233,53 +269,96 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (c.diagnostics && last) a.nfev[e] = nf;
                 if (st) a.status[e] |= (uint8_t)st;
                 if (c.autoreset && (term || trunc)) {
-                    ls.episodes += 1; ls.length += ep_len; ls.crashed += term; ls.truncated += (trunc && !term);
-                    ls.ret0 += (double)ep_ret[0]; ls.ret1 += (double)ep_ret[1]; ls.ret0sq += (double)ep_ret[0] * (double)ep_ret[0];
+                    ep_len_done = ep_len; ret_done0 = ep_ret[0]; ret_done1 = ep_ret[1];
                     if (last) {
 #pragma unroll
                         for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
                     }
                     ep_idx += 1;
-                    float o2[23];
-                    auto_reset_env<T, MODE>(&a, e, ep_idx, o2);
-#pragma unroll
-                    for (int i = 0; i < O; ++i) o[i] = o2[i];
+                    // the reset lane writes its own (new-episode) observation row; it is left out of the tile copy
+                    float* r1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (last ? a.obs + e * O : nullptr);
+                    float* r2 = (a.obs_roll && last) ? a.obs + e * O : nullptr;
+                    auto_reset_env<T, MODE>(&a, e, ep_idx, r1, r2);
                     ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
                     did_reset = true;
                 }
             }
-            // ---- observation rows: registers -> shared tile (row = env & 31) -> global, 128-byte lines.
-            // Finished lanes usually belong to one 32-env tile and one sub-step; stragglers (lanes that needed
-            // another attempt) belong to an older tile and are flushed in a further round of this loop.
-            unsigned rem = finmask;
+            __syncwarp();
+            // ---- statistics of the finished lanes: votes and REDUX, accumulated by lane 0 in shared memory ----
+            {
+                const int att = (nf - 2) / 12;
+                const int s_nfev = __reduce_add_sync(FULL, nf);
+                const int s_proj = __reduce_add_sync(FULL, nproj);
+                const unsigned m1 = __ballot_sync(FULL, fin && att == 1), m2 = __ballot_sync(FULL, fin && att == 2);
+                const unsigned m3 = __ballot_sync(FULL, fin && att == 3), m4 = __ballot_sync(FULL, fin && att >= 4);
+                const unsigned mbad = __ballot_sync(FULL, fin && st != 0);
+                const float s_rew = warp_sum_f(rew0f);
+                const unsigned mres = __ballot_sync(FULL, did_reset);
+                if (lane == 0) {
+                    ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev; ws[15] += (double)s_proj;
+                    ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
+                    ws[8] += (double)__popc(mbad); ws[14] += (double)s_rew;
+                }
+                if (mres) {   // once per episode
+                    const int s_len = __reduce_add_sync(FULL, ep_len_done);
+                    const unsigned mterm = __ballot_sync(FULL, did_reset && term);
+                    const double r0 = warp_sum(did_reset ? (double)ret_done0 : 0.0);
+                    const double r1 = warp_sum(did_reset ? (double)ret_done1 : 0.0);
+                    const double r0sq = warp_sum(did_reset ? (double)ret_done0 * (double)ret_done0 : 0.0);
+                    if (lane == 0) {
+                        ws[0] += (double)__popc(mres); ws[3] += (double)s_len; ws[4] += (double)__popc(mterm);
+                        ws[5] += (double)(__popc(mres) - __popc(mterm)); ws[1] += r0; ws[2] += r1; ws[6] += r0sq;
+                    }
+                }
+            }
+            // ---- observation rows: shared tile (row = lane) -> global.  Finished lanes are grouped by
+            // (32-env tile, sub-step); a group is written as O coalesced 128-byte stores through the
+            // row -> lane map, rows that are not part of the group masked out.  Stragglers (lanes that
+            // needed another attempt) belong to an older tile and are flushed in a further round.
+            unsigned rem = finmask & ~__ballot_sync(FULL, did_reset);
+            const int myrow = (int)(e & 31);
             while (rem) {
                 const int lead = __ffs(rem) - 1;
-                const int64_t tb = __shfl_sync(0xffffffffu, e & ~(int64_t)31, lead);
-                const int kk = __shfl_sync(0xffffffffu, k, lead);
-                const bool mine = fin && ((e & ~(int64_t)31) == tb) && (k == kk);
-                const unsigned grp = __ballot_sync(0xffffffffu, mine);
-                const unsigned rows = __reduce_or_sync(0xffffffffu, mine ? (1u << (int)(e & 31)) : 0u);
+                const int64_t tb = __shfl_sync(FULL, e & ~(int64_t)31, lead);
+                const int kk = __shfl_sync(FULL, k, lead);
+                const bool mine = fin && !did_reset && ((e & ~(int64_t)31) == tb) && (k == kk);
+                const unsigned grp = __ballot_sync(FULL, mine);
                 rem &= ~grp;
-                if (mine) {
-                    float* row = os + (int)(e & 31) * O;
-#pragma unroll
-                    for (int i = 0; i < O; ++i) row[i] = o[i];
-                }
-                __syncwarp();
                 const bool lst = (kk == a.n_steps - 1);
                 float* d1 = a.obs_roll ? a.obs_roll + ((int64_t)kk * N + tb) * O : (lst ? a.obs + tb * O : nullptr);
                 float* d2 = (a.obs_roll && lst) ? a.obs + tb * O : nullptr;
+                if (__popc(grp) > 8) {
+                    // flat pass over the shared tile in source order: element q = it*32 + lane belongs to source
+                    // lane q / O (advanced without dividing); its tile row comes from that lane by shuffle.  Lanes
+                    // take consecutive envs, so consecutive sources have consecutive rows: full-line stores.
+                    int sl = lane / O, col = lane - sl * O;
 #pragma unroll 1
-                for (int q = lane; q < 32 * O; q += 32) {
-                    const int r_ = q / O;
-                    if ((rows >> r_) & 1u) {
-                        const float v = os[q];
-                        if (d1) d1[q] = v;
-                        if (d2) d2[q] = v;
+                    for (int it = 0; it < O; ++it) {
+                        const int drow = __shfl_sync(FULL, myrow, sl);
+                        if ((grp >> sl) & 1u) {
+                            const float v = os[it * 32 + lane];
+                            const int di = drow * O + col;
+                            if (d1) d1[di] = v;
+                            if (d2) d2[di] = v;
+                        }
+                        col += 32 - O; sl += 1;
+                        if (col >= O) { col -= O; sl += 1; }
+                    }
+                } else {
+                    unsigned rr = grp;
+                    while (rr) {
+                        const int sl = __ffs(rr) - 1;
+                        rr &= rr - 1;
+                        const int drow = __shfl_sync(FULL, myrow, sl);
+                        if (lane < O) {
+                            const float v = os[sl * O + lane];
+                            if (d1) d1[drow * O + lane] = v;
+                            if (d2) d2[drow * O + lane] = v;
+                        }
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
             if (fin) {
                 fin = false;
                 if (did_reset) {
@@ -291,8 +370,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     y[12] = a.state[15 * N + e]; y[13] = a.state[16 * N + e]; W3 = a.state[17 * N + e];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) I[i] = a.integ[i * N + e];
-                    p_m = a.params[0 * N + e]; p_d = a.params[1 * N + e]; p_J1 = a.params[2 * N + e];
-                    p_J3 = a.params[3 * N + e]; p_ctf = a.params[4 * N + e]; p_ctw = a.params[5 * N + e];
+                    p_m = a.params[0 * N + e]; p_J1 = a.params[2 * N + e]; p_J3 = a.params[3 * N + e]; p_ctw = a.params[5 * N + e];
+                    if (MODE == 0) { p_d = a.params[1 * N + e]; p_ctf = a.params[4 * N + e]; }
                 }
                 k += 1;
                 if (k < a.n_steps) need_init = true;
@@ -315,7 +394,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         }
         // ---- A2: idle lanes take the next envs of the warp's sequence ----
         {
-            const unsigned need = __ballot_sync(0xffffffffu, !busy);
+            const unsigned need = __ballot_sync(FULL, !busy);
             if (need && cursor < vlen) {
                 const int rank = __popc(need & ((1u << lane) - 1u));
                 const int64_t v = cursor + rank;
@@ -332,17 +411,35 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         y[12] = a.state[15 * N + e]; y[13] = a.state[16 * N + e]; W3 = a.state[17 * N + e];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) I[i] = a.integ[i * N + e];
-                        p_m = a.params[0 * N + e]; p_d = a.params[1 * N + e]; p_J1 = a.params[2 * N + e];
-                        p_J3 = a.params[3 * N + e]; p_ctf = a.params[4 * N + e]; p_ctw = a.params[5 * N + e];
+                        p_m = a.params[0 * N + e]; p_J1 = a.params[2 * N + e]; p_J3 = a.params[3 * N + e]; p_ctw = a.params[5 * N + e];
+                        if (MODE == 0) { p_d = a.params[1 * N + e]; p_ctf = a.params[4 * N + e]; }
                         ep_ret[0] = a.ep_return[e];
                         ep_ret[1] = (G == 2) ? a.ep_return[N + e] : (T)0;
                         ep_len = a.ep_length[e];
                         ep_idx = a.ep_index[e];
+#if QR_OPT_PREFETCH
+                        // L2 prefetch of what this env.step reads later (goal rows, actions) ...
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) prefetch_l2(a.goal + i * N + e);
+                        if (a.actions) prefetch_l2((const char*)a.actions + (size_t)e * A * (a.act_f32 ? 4 : 8));
+                        // ... and of the env this lane will most likely take next (same lane of the next tile)
+                        const int64_t vn = v + 32;
+                        const int64_t en = a.env_lo + ((gw + (vn >> 5) * W) << 5) + (vn & 31);
+                        if (vn < vlen && en < a.env_hi) {
+#pragma unroll
+                            for (int i = 0; i < 18; ++i) prefetch_l2(a.state + i * N + en);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) prefetch_l2(a.integ + i * N + en);
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) prefetch_l2(a.params + i * N + en);
+                            prefetch_l2(a.ep_return + en); prefetch_l2(a.ep_length + en); prefetch_l2(a.ep_index + en);
+                        }
+#endif
                     }
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, busy)) break;
+        if (!__any_sync(FULL, busy)) break;
         // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
         if (busy && need_init) {
             need_init = false;
@@ -428,22 +525,16 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             ode.nproj += fl & 1;
         }
         // =============================== phase B ===============================
-        if (busy && !fin) fin = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, lane);
+        {
+            const bool live = busy && !fin;
+            const bool f2 = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, lane, live);
+            if (live) fin = f2;
+        }
     }
 
-    // ---- statistics: warp shuffle reduce -> one shared atomic per warp -> one global atomic per block ----
-    {
-        double v[16] = {(double)ls.episodes, ls.ret0, ls.ret1, (double)ls.length, (double)ls.crashed, (double)ls.truncated,
-                        ls.ret0sq, (double)ls.steps, (double)ls.bad, (double)ls.nfev, (double)ls.a1, (double)ls.a2,
-                        (double)ls.a3, (double)ls.a4, ls.rew0, (double)ls.proj};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            double s = warp_sum(v[i]);
-            if (lane == 0 && s != 0.0) atomicAdd(&s_stats[i], s);
-        }
-        __syncthreads();
-        if (threadIdx.x < 16 && s_stats[threadIdx.x] != 0.0) atomicAdd(&a.stats[threadIdx.x], s_stats[threadIdx.x]);
-    }
+    // ---- flush this warp's statistics: one atomic per non-zero statistic ----
+    __syncwarp();
+    if (lane < 16 && ws[lane] != 0.0) atomicAdd(&a.stats[lane], ws[lane]);
 }
 
 // ---- env.reset(env_type) -----------------------------------------------------------------------------------

@@ -70,6 +70,7 @@ template <typename T> qr::StepArgs<T> make_args(const qr_handle* h)
     a.c.nCIb1 = (float)(-c.CIb1); a.c.nCW = (float)(-c.CW); a.c.nCw12 = (float)(-c.Cw12); a.c.nCW3 = (float)(-c.CW3);
     a.c.Cx = c.Cx; a.c.Cv = c.Cv; a.c.Cb1 = c.Cb1; a.c.CW = c.CW;
     a.c.rmin = c.reward_min; a.c.rmin1 = c.reward_min_1; a.c.rmin2 = c.reward_min_2; a.c.udm = c.udm_pct;
+    a.c.slope = 1.0 / (0.0 - c.reward_min); a.c.slope1 = 1.0 / (0.0 - c.reward_min_1); a.c.slope2 = 1.0 / (0.0 - c.reward_min_2);
     a.c.mode = c.mode; a.c.integrator = c.integrator; a.c.autoreset = c.autoreset; a.c.goal_mode = c.goal_mode;
     a.c.env_type = c.env_type; a.c.max_episode_steps = c.max_episode_steps; a.c.diagnostics = c.reserved0;
     a.n = c.n_envs; a.env_lo = 0; a.env_hi = c.n_envs; a.env_id_offset = c.env_id_offset;
@@ -94,7 +95,7 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     a.actions = actions; a.act_f32 = (act_dtype == QR_F32); a.n_steps = n_steps;
     a.obs_roll = obs_roll; a.reward_roll = (T*)reward_roll; a.done_roll = done_roll;
     // persistent warps: one CTA per SM, as many warps as the stage storage in shared memory allows
-    const size_t per_warp = (size_t)qr::QR_NSLOTS * qr::QR_SLOT_ELEMS * sizeof(T) + 32 * 24 * sizeof(float);
+    const size_t per_warp = qr::warp_smem<T>::bytes;
     int warps = (int)((size_t)h->smem_optin / per_warp);
     if (warps > qr::step_threads<T>::value / 32) warps = qr::step_threads<T>::value / 32;
     if (warps < 1) return fail(QR_ERR_CUDA, "not enough shared memory per block for the step kernel");
@@ -194,7 +195,7 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     QR_CUDA(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
     QR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     QR_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    h->smem_optin -= 1024;   // static shared memory of the kernel + reserve
+    h->smem_optin -= 256;    // reserve
     {
         static bool tab_done[64] = {false};
         if (!tab_done[device & 63]) {
