@@ -130,6 +130,33 @@ template <typename T> QR_DEV void ks_store_lane(T* col, int lane, const T* k)
     }
 }
 
+// acc[0..13] += c * k[0..13].  float32 on sm_100a: seven packed FFMA2 (fma.rn.f32x2) instead of fourteen FFMA --
+// the kernel is issue bound, not FMA-pipe bound, so halving the instruction count of the stage sums pays.
+#ifndef QR_OPT_FFMA2
+#define QR_OPT_FFMA2 1
+#endif
+template <typename T> QR_DEV void axpy14(T c, const T* k, T* acc)
+{
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = num<T>::fma(c, k[i], acc[i]);
+}
+#if QR_OPT_FFMA2
+template <> QR_DEV void axpy14<float>(float c, const float* k, float* acc)
+{
+    const float2 cc = make_float2(c, c);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        float2 r = __ffma2_rn(cc, make_float2(k[2 * i], k[2 * i + 1]), make_float2(acc[2 * i], acc[2 * i + 1]));
+        acc[2 * i] = r.x; acc[2 * i + 1] = r.y;
+    }
+}
+#endif
+// three weighted sums at once (y_new and the two error estimators)
+template <typename T> QR_DEV void axpy14x3(T b, T e5, T e3, const T* k, T* sb, T* s5, T* s3)
+{
+    axpy14<T>(b, k, sb); axpy14<T>(e5, k, s5); axpy14<T>(e3, k, s3);
+}
+
 // Layout of the 14 integrated components kept in registers: y[0..2] = v, y[3..11] = R (column-major),
 // y[12..13] = W1, W2.  x[3] and W3 are carried separately.
 template <typename T> struct Dyn {
@@ -272,7 +299,8 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         {
             const T ha0 = h * TB::A(s, 0);
 #pragma unroll
-            for (int i = 0; i < 14; ++i) ys[i] = N::fma(ha0, K0[i], y[i]);
+            for (int i = 0; i < 14; ++i) ys[i] = y[i];
+            axpy14<T>(ha0, K0, ys);
         }
         const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
         int j = jlo;
@@ -283,8 +311,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
             T k0[14], k1[14];
             ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k0);
             ks_load_lane<T>(kl + k_slot(j + 1) * QR_SLOT_ELEMS, lane, k1);
-#pragma unroll
-            for (int i = 0; i < 14; ++i) ys[i] = N::fma(c1, k1[i], N::fma(c0, k0[i], ys[i]));
+            axpy14<T>(c0, k0, ys); axpy14<T>(c1, k1, ys);
         }
         if (j < s) {
 #else
@@ -294,8 +321,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
             const T c = h * TB::A(s, j);
             T k[14];
             ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k);
-#pragma unroll
-            for (int i = 0; i < 14; ++i) ys[i] = N::fma(c, k[i], ys[i]);
+            axpy14<T>(c, k, ys);
         }
         const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
         if (s >= 5) {
@@ -323,8 +349,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         const T bj = TB::B(j), e5j = TB::E5(j), e3j = TB::E3(j);
         T k[14];
         ks_load_lane<T>(kl + (j - 3) * QR_SLOT_ELEMS, lane, k);
-#pragma unroll
-        for (int i = 0; i < 14; ++i) { sb[i] = N::fma(bj, k[i], sb[i]); s5[i] = N::fma(e5j, k[i], s5[i]); s3[i] = N::fma(e3j, k[i], s3[i]); }
+        axpy14x3<T>(bj, e5j, e3j, k, sb, s5, s3);
     }
     T e5n = 0, e3n = 0;
     T xnew[3];

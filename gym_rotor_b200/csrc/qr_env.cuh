@@ -76,55 +76,64 @@ template <typename T> struct EnvRegs {
 
 // ---- env.reset(env_type) with counter-based randomness ---------------------------------------------------
 // Uniform order: m d J1 J3 c_tf c_tw | yaw | origin-spawn coin | x(3) | v(3) | W(3) | roll pitch | theta(goal)
-// All reset arithmetic is float64 regardless of T (resets are rare), then cast.
+// The arithmetic runs in T: float64 mode reproduces the oracle's reset to rounding; float32 mode keeps the
+// (once per episode, divergent) reset path cheap.
+template <typename T> QR_DEV T u01t(uint32_t k)
+{
+    if (sizeof(T) == 8) return (T)(((double)k + 0.5) * 2.3283064365386963e-10);
+    return (T)(((float)(k >> 8) + 0.5f) * 5.9604644775390625e-8f);   // 24 bits: exact in float32, never 0 or 1
+}
+template <typename T> QR_DEV void sincos_t(T a, T* s, T* c);
+template <> QR_DEV void sincos_t<double>(double a, double* s, double* c) { sincos(a, s, c); }
+template <> QR_DEV void sincos_t<float>(float a, float* s, float* c) { sincosf(a, s, c); }
+
 template <typename T>
-QR_DEV void reset_env(EnvRegs<T>& e, const Philox& ph, uint64_t gid, uint32_t episode, int env_type, double udm, double* theta_out)
+QR_DEV void reset_env(EnvRegs<T>& e, const Philox& ph, uint64_t gid, uint32_t episode, int env_type, double udm, T* theta_out)
 {
     uint32_t r[20];
 #pragma unroll
     for (int j = 0; j < 5; ++j) ph((uint32_t)gid, (uint32_t)(gid >> 32), episode, QR_DOMAIN_RESET + j, r + 4 * j);
-    const double m0 = 2.15, d0 = 0.23, J10 = 0.022, J30 = 0.035, ctf0 = 0.0135, ctw0 = 2.2;  // quad.py:28-32
-    double p[6] = {m0, d0, J10, J30, ctf0, ctw0};
+    const T nom[6] = {(T)2.15, (T)0.23, (T)0.022, (T)0.035, (T)0.0135, (T)2.2};  // quad.py:28-32
+    T p[6] = {nom[0], nom[1], nom[2], nom[3], nom[4], nom[5]};
     if (env_type == 0) {
-        double rr = udm / 100.0;
-        const double nom[6] = {m0, d0, J10, J30, ctf0, ctw0};
+        const T rr = (T)(udm / 100.0);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            double w = (j == 5) ? nom[j] * (rr / 2.) : nom[j] * rr;  // c_tw: half the range (quad.py:375)
-            double lo = nom[j] - w, hi = nom[j] + w;
-            p[j] = lo + (hi - lo) * u01(r[j]);
+            T w = (j == 5) ? nom[j] * (rr / (T)2) : nom[j] * rr;  // c_tw: half the range (quad.py:375)
+            T lo = nom[j] - w, hi = nom[j] + w;
+            p[j] = lo + (hi - lo) * u01t<T>(r[j]);
         }
     }
-    const double PI = 3.14159265358979323846;
-    double yaw = -PI + (PI - (-PI)) * u01(r[6]);
-    double ix, iv, iR, iW;
+    const T PI = (T)3.14159265358979323846;
+    T yaw = -PI + (PI - (-PI)) * u01t<T>(r[6]);
+    T ix, iv, iR, iW;
     if (env_type == 0) {
-        if (u01(r[7]) < 0.2) { ix = 0; iv = 0; iR = 0; iW = 0; }                       // quad.py:342-346
-        else { ix = 0.6; iv = 4.0 * 0.5; iR = 50 * (PI / 180.); iW = 2 * PI * 0.5; }   // quad.py:347-351
-    } else { ix = 0.4; iv = 0; iR = 0; iW = 0; }                                       // quad.py:352-356
-    double xs[3], vs[3], Ws[3];
+        if (u01t<T>(r[7]) < (T)0.2) { ix = 0; iv = 0; iR = 0; iW = 0; }                              // quad.py:342-346
+        else { ix = (T)0.6; iv = (T)4.0 * (T)0.5; iR = (T)50 * (PI / (T)180); iW = (T)2 * PI * (T)0.5; }  // quad.py:347-351
+    } else { ix = (T)0.4; iv = 0; iR = 0; iW = 0; }                                                 // quad.py:352-356
+    T xs[3], vs[3], Ws[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        xs[i] = -ix + (ix - (-ix)) * u01(r[8 + i]);
-        vs[i] = -iv + (iv - (-iv)) * u01(r[11 + i]);
-        Ws[i] = -iW + (iW - (-iW)) * u01(r[14 + i]);
+        xs[i] = -ix + (ix - (-ix)) * u01t<T>(r[8 + i]);
+        vs[i] = -iv + (iv - (-iv)) * u01t<T>(r[11 + i]);
+        Ws[i] = -iW + (iW - (-iW)) * u01t<T>(r[14 + i]);
     }
-    double roll = -iR + (iR - (-iR)) * u01(r[17]), pitch = -iR + (iR - (-iR)) * u01(r[18]);
-    double sr, cr, sp, cp, sy, cy;
-    sincos(roll, &sr, &cr); sincos(pitch, &sp, &cp); sincos(yaw, &sy, &cy);
+    T roll = -iR + (iR - (-iR)) * u01t<T>(r[17]), pitch = -iR + (iR - (-iR)) * u01t<T>(r[18]);
+    T sr, cr, sp, cp, sy, cy;
+    sincos_t<T>(roll, &sr, &cr); sincos_t<T>(pitch, &sp, &cp); sincos_t<T>(yaw, &sy, &cy);
     // R = Rz(yaw) Ry(pitch) Rx(roll)   (Rotation.from_euler('xyz'), quad.py:199)
-    double R[9] = {cy * cp, sy * cp, -sp,
-                   cy * sp * sr - sy * cr, sy * sp * sr + cy * cr, cp * sr,
-                   cy * sp * cr + sy * sr, sy * sp * cr - cy * sr, cp * cr};
+    T R[9] = {cy * cp, sy * cp, -sp,
+              cy * sp * sr - sy * cr, sy * sp * sr + cy * cr, cp * sr,
+              cy * sp * cr + sy * sr, sy * sp * cr - cy * sr, cp * cr};
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { e.x[i] = (T)xs[i]; e.y[i] = (T)vs[i]; }
+    for (int i = 0; i < 3; ++i) { e.x[i] = xs[i]; e.y[i] = vs[i]; }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) e.y[3 + i] = (T)R[i];
-    e.y[12] = (T)Ws[0]; e.y[13] = (T)Ws[1]; e.W3 = (T)Ws[2];
+    for (int i = 0; i < 9; ++i) e.y[3 + i] = R[i];
+    e.y[12] = Ws[0]; e.y[13] = Ws[1]; e.W3 = Ws[2];
 #pragma unroll
     for (int i = 0; i < 8; ++i) e.I[i] = (T)0;
-    e.m = (T)p[0]; e.d = (T)p[1]; e.J1 = (T)p[2]; e.J3 = (T)p[3]; e.c_tf = (T)p[4]; e.c_tw = (T)p[5];
-    *theta_out = (-25.0 + 50.0 * u01(r[19])) * (PI / 180.);   // trajectory_generator.py:144
+    e.m = p[0]; e.d = p[1]; e.J1 = p[2]; e.J3 = p[3]; e.c_tf = p[4]; e.c_tw = p[5];
+    *theta_out = ((T)-25 + (T)50 * u01t<T>(r[19])) * (PI / (T)180);   // trajectory_generator.py:144
 }
 
 // ---- goal generator, mode 0 ---------------------------------------------------------------------------------
@@ -152,21 +161,22 @@ template <typename T> QR_DEV void traj_wd(const T* R, const T* W, const T* b1d, 
 
 // mark_traj_start + first get_desired(mode 0) on the float32-cast reset state (main.py:226-229):
 // xd = vd = 0, b1d = Rz(theta) [cos psi, sin psi, 0], psi = heading of b1; Wd from that same f32 state.
-template <typename T> QR_DEV void init_goal_mode0(EnvRegs<T>& e, double theta)
+template <typename T> QR_DEV void init_goal_mode0(EnvRegs<T>& e, T theta)
 {
-    double R[9], W[3];
+    T R[9], W[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = (double)(float)e.y[3 + i];
-    W[0] = (double)(float)e.y[12]; W[1] = (double)(float)e.y[13]; W[2] = (double)(float)e.W3;
-    ensure_so3<double>(R);
-    double psi = atan2(R[1], R[0]);
-    double cps = cos(psi), sps = sin(psi), cth = cos(theta), sth = sin(theta);
-    double b1d[3] = {cth * cps - sth * sps, sth * cps + cth * sps, 0.0};
-    double Wd[3];
-    traj_wd<double>(R, W, b1d, Wd);
+    for (int i = 0; i < 9; ++i) R[i] = (T)(float)e.y[3 + i];
+    W[0] = (T)(float)e.y[12]; W[1] = (T)(float)e.y[13]; W[2] = (T)(float)e.W3;
+    ensure_so3<T>(R);
+    T psi = num<T>::atan2(R[1], R[0]);
+    T sps, cps, sth, cth;
+    sincos_t<T>(psi, &sps, &cps); sincos_t<T>(theta, &sth, &cth);
+    T b1d[3] = {cth * cps - sth * sps, sth * cps + cth * sps, (T)0};
+    T Wd[3];
+    traj_wd<T>(R, W, b1d, Wd);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        e.goal[i] = 0; e.goal[3 + i] = 0; e.goal[6 + i] = (T)b1d[i]; e.goal[9 + i] = (T)Wd[i];
+        e.goal[i] = 0; e.goal[3 + i] = 0; e.goal[6 + i] = b1d[i]; e.goal[9 + i] = Wd[i];
     }
 }
 

@@ -102,7 +102,7 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
     const Philox ph{a.key0, a.key1};
     const uint64_t gid = (uint64_t)(a.env_id_offset + e);
     EnvRegs<T> r;
-    double theta;
+    T theta;
     reset_env<T>(r, ph, gid, episode, c.env_type, c.udm, &theta);
     if (c.goal_mode == 1) init_goal_mode0<T>(r, theta);
     else {
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(QR_BLOCK) k_reset(const StepArgs<T> a, const u
     const uint64_t gid = (uint64_t)(a.env_id_offset + e);
     EnvRegs<T> r;
     uint32_t ep = a.ep_index[e] + 1;
-    double theta;
+    T theta;
     reset_env<T>(r, ph, gid, ep, env_type, a.c.udm, &theta);
     store_state(r, a, e);
     store_params_goal(r, a, e, true, false);
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(QR_BLOCK) k_init_goal(const StepArgs<T> a, con
     load_env(r, a, e);
     uint32_t rnd[4];
     ph((uint32_t)gid, (uint32_t)(gid >> 32), a.ep_index[e], QR_DOMAIN_RESET + 4u, rnd);
-    double theta = (-25.0 + 50.0 * u01(rnd[3])) * (3.14159265358979323846 / 180.);
+    T theta = ((T)-25 + (T)50 * u01t<T>(rnd[3])) * ((T)3.14159265358979323846 / (T)180);
     init_goal_mode0<T>(r, theta);
     store_params_goal(r, a, e, false, true);
 }
