@@ -169,16 +169,28 @@ def run_ours(args):
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     n = args.envs_per_gpu
     env = vec_env.BatchedQuadEnv(n, framework=fw, dtype=dtype, device=dev, seed=args.seed, autoreset=True,
-                                 goal_mode="traj0", env_type="train", max_episode_steps=4000,
+                                 goal_mode="traj0" if fw != "QUAD" else "external", env_type="train", max_episode_steps=4000,
                                  env_id_offset=rank * n, diagnostics=False)
-    env.reset(); env.init_goal(); env.get_norm_error_state()
+    env.reset()
+    if fw != "QUAD":
+        env.init_goal()
+    env.get_norm_error_state()
     A = env.act_dim
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-    pool = [torch.rand((n, A), device=dev, dtype=torch.float32, generator=gen) * 2 - 1 for _ in range(4)]
+    if args.actions == "zero":   # hover-like thrust, no torque: the single-attempt, no-reset regime of a trained policy
+        pool = [torch.zeros((n, A), device=dev, dtype=torch.float32) for _ in range(2)]
+        for p in pool:
+            p[:, 0] = -0.06
+    else:
+        pool = [torch.rand((n, A), device=dev, dtype=torch.float32, generator=gen) * 2 - 1 for _ in range(4)]
     stats_total = np.zeros(16)
+    fused = max(1, args.fused)
 
     def one_step(i):
-        env.step(pool[i % len(pool)])
+        if fused > 1:
+            env.rollout(fused)      # `fused` env.step() calls in one launch, Philox actions drawn in-kernel
+        else:
+            env.step(pool[i % len(pool)])
         if (i + 1) % STATS_EVERY == 0:
             return allreduce_stats(env, dev) if world > 1 else env.stats()
         return None
@@ -211,7 +223,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    total_steps = float(n) * world * args.steps
+    total_steps = float(n) * world * args.steps * fused
     value = total_steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer entry point (qr_step_host): pinned host actions in, obs/reward/done out
@@ -242,8 +254,8 @@ def run_ours(args):
         key = "%s_%s" % (fw, args.dtype)
         bytes_per = ALG_BYTES.get(key, 366)
         kernel_ms = ms / args.steps
-        ach_gbs = bytes_per * n / (kernel_ms * 1e-3) / 1e9
-        per_gpu_steps = n / (kernel_ms * 1e-3)
+        ach_gbs = bytes_per * n * fused / (kernel_ms * 1e-3) / 1e9
+        per_gpu_steps = n * fused / (kernel_ms * 1e-3)
         fp_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12 * (0.5 if args.dtype == "f64" else 1.0)
         attempts = stats_total[10:14]
         mean_att = float((attempts * np.array([1, 2, 3, 4])).sum() / max(1.0, attempts.sum()))
@@ -255,7 +267,7 @@ def run_ours(args):
                                    "on-device trajgen mode-0 goals, in-kernel auto reset (4000-step limit), "
                                    "stats all-reduce every %d steps" % (
                                        {"MONO": "CoupledWrapper", "MODUL": "DecoupledWrapper", "QUAD": "Quad-v0"}[fw], n, STATS_EVERY),
-                       "envs_per_gpu": n, "framework": fw,
+                       "envs_per_gpu": n, "framework": fw, "actions": args.actions, "fused_steps_per_launch": fused,
                        "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2)" % (bytes_per * n / 1e6),
                        "mean_dop853_attempts": mean_att, "episodes": stats_total[0],
                        "mean_episode_length": float(stats_total[3] / max(1.0, stats_total[0]))},
@@ -295,6 +307,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1992)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--actions", default="random", choices=["random", "zero"])
+    ap.add_argument("--fused", type=int, default=1, help="env.step() calls fused per launch (qr_rollout, in-kernel actions)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
