@@ -168,13 +168,13 @@ template <typename T> struct Dyn {
 };
 
 // One right-hand-side evaluation at stage point (ys, W3s) -> k[14].  Returns ensure_SO3 flags.
-template <typename T> QR_DEV int rhs14(const T* ys, T W3s, const Dyn<T>& d, T* k)
+template <typename T, bool NEWTON = false> QR_DEV int rhs14(const T* ys, T W3s, const Dyn<T>& d, T* k)
 {
     using N = num<T>;
     T R[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = ys[3 + i];
-    int fl = ensure_so3<T>(R);  // state_decomposition -> ensure_SO3 on every call (quad_utils.py:12-16)
+    int fl = ensure_so3<T, NEWTON>(R);  // state_decomposition -> ensure_SO3 on every call (quad_utils.py:12-16)
     const T W0 = ys[12], W1 = ys[13], W2 = W3s;
     // v' = g e3 - (f/m) R e3
     k[0] = -d.fm * R[6];
@@ -239,7 +239,7 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
 #pragma unroll
     for (int i = 0; i < 14; ++i) y1[i] = N::fma(h0, K0[i], y[i]);
     T W31 = N::fma(h0, d.w3dot, W3);
-    fl = rhs14<T>(y1, W31, d, k1);
+    fl = rhs14<T, true>(y1, W31, d, k1);
     o.nproj += fl & 1; if (fl & 2) o.status |= 4;
     T s2 = 0;
 #pragma unroll
@@ -304,7 +304,23 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         }
         const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
         int j = jlo;
-#if QR_OPT_PAIR2
+#if QR_OPT_PAIR2 == 2
+        // software pipelined: the next K vector is in flight while the current one is accumulated
+        if (j < s) {
+            T ka[14], kb[14];
+            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, ka);
+            T ca = h * TB::A(s, j);
+#pragma unroll 1
+            for (; j < s; j += 2) {
+                const bool has_b = j + 1 < s;
+                T cb = 0;
+                if (has_b) { ks_load_lane<T>(kl + k_slot(j + 1) * QR_SLOT_ELEMS, lane, kb); cb = h * TB::A(s, j + 1); }
+                axpy14<T>(ca, ka, ys);
+                if (j + 2 < s) { ks_load_lane<T>(kl + k_slot(j + 2) * QR_SLOT_ELEMS, lane, ka); ca = h * TB::A(s, j + 2); }
+                if (has_b) axpy14<T>(cb, kb, ys);
+            }
+        }
+#elif QR_OPT_PAIR2 == 1
 #pragma unroll 1
         for (; j + 1 < s; j += 2) {   // two K vectors in flight per trip
             const T c0 = h * TB::A(s, j), c1 = h * TB::A(s, j + 1);
@@ -314,15 +330,20 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
             axpy14<T>(c0, k0, ys); axpy14<T>(c1, k1, ys);
         }
         if (j < s) {
-#else
-#pragma unroll 1
-        for (; j < s; ++j) {
-#endif
             const T c = h * TB::A(s, j);
             T k[14];
             ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k);
             axpy14<T>(c, k, ys);
         }
+#else
+#pragma unroll 1
+        for (; j < s; ++j) {
+            const T c = h * TB::A(s, j);
+            T k[14];
+            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k);
+            axpy14<T>(c, k, ys);
+        }
+#endif
         const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
         if (s >= 5) {
             const T bs = TB::B(s), e5s = TB::E5(s), e3s = TB::E3(s);

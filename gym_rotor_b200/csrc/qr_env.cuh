@@ -85,7 +85,9 @@ template <typename T> QR_DEV T u01t(uint32_t k)
 }
 template <typename T> QR_DEV void sincos_t(T a, T* s, T* c);
 template <> QR_DEV void sincos_t<double>(double a, double* s, double* c) { sincos(a, s, c); }
-template <> QR_DEV void sincos_t<float>(float a, float* s, float* c) { sincosf(a, s, c); }
+// float32 mode: arguments are bounded by pi, so the range-reduction slow path of sincosf is dead weight
+// (hundreds of instructions in a divergent path); __sincosf is accurate to ~4e-7 there
+template <> QR_DEV void sincos_t<float>(float a, float* s, float* c) { __sincosf(a, s, c); }
 
 template <typename T>
 QR_DEV void reset_env(EnvRegs<T>& e, const Philox& ph, uint64_t gid, uint32_t episode, int env_type, double udm, T* theta_out)

@@ -14,6 +14,9 @@
 #ifndef QR_OPT_PREFETCH
 #define QR_OPT_PREFETCH 0
 #endif
+#ifndef QR_OPT_LOCKSTEP
+#define QR_OPT_LOCKSTEP 0
+#endif
 
 namespace qr {
 
@@ -93,7 +96,7 @@ QR_DEV double warp_sum(double v)
 // (main.py:226-230).  Works through global memory so that the hot loop's registers are not affected; the
 // caller re-loads the env afterwards.  `o` receives the first observation of the new episode.
 template <typename T, int MODE>
-__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* dst1, float* dst2)
+__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* dst1, float* dst2, T* scratch)
 {
     const StepArgs<T>& a = *ap;
     constexpr int O = (MODE == 1) ? 23 : 18;
@@ -118,7 +121,17 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
     } else {
         norm_error_state<T>(r, c, o, MODE);   // first obs of the new episode; advances the integrals once
     }
-    store_state(r, a, e);
+    // new state / integrals / parameters go back to the caller through its shared scratch (the caller keeps
+    // them in registers and writes the state arrays when it releases the env); parameters and the goal are
+    // only ever written here
+#pragma unroll
+    for (int i = 0; i < 3; ++i) scratch[i] = r.x[i];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) scratch[3 + i] = r.y[i];
+    scratch[17] = r.W3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) scratch[18 + i] = r.I[i];
+    scratch[26] = r.m; scratch[27] = r.d; scratch[28] = r.J1; scratch[29] = r.J3; scratch[30] = r.c_tf; scratch[31] = r.c_tw;
     store_params_goal(r, a, e, true, c.goal_mode == 1);
 #pragma unroll
     for (int i = 0; i < O; ++i) {
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     // the reset lane writes its own (new-episode) observation row; it is left out of the tile copy
                     float* r1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (last ? a.obs + e * O : nullptr);
                     float* r2 = (a.obs_roll && last) ? a.obs + e * O : nullptr;
-                    auto_reset_env<T, MODE>(&a, e, ep_idx, r1, r2);
+                    auto_reset_env<T, MODE>(&a, e, ep_idx, r1, r2, ks + lane * 32);   // the stage storage is free in phase A
                     ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
                     did_reset = true;
                 }
@@ -362,16 +375,16 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             if (fin) {
                 fin = false;
                 if (did_reset) {
-                    // re-load what the reset wrote through global memory
+                    const T* sc = ks + lane * 32;   // what auto_reset_env left in this lane's scratch
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) x[i] = a.state[i * N + e];
+                    for (int i = 0; i < 3; ++i) x[i] = sc[i];
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) y[i] = a.state[(3 + i) * N + e];
-                    y[12] = a.state[15 * N + e]; y[13] = a.state[16 * N + e]; W3 = a.state[17 * N + e];
+                    for (int i = 0; i < 14; ++i) y[i] = sc[3 + i];
+                    W3 = sc[17];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) I[i] = a.integ[i * N + e];
-                    p_m = a.params[0 * N + e]; p_J1 = a.params[2 * N + e]; p_J3 = a.params[3 * N + e]; p_ctw = a.params[5 * N + e];
-                    if (MODE == 0) { p_d = a.params[1 * N + e]; p_ctf = a.params[4 * N + e]; }
+                    for (int i = 0; i < 8; ++i) I[i] = sc[18 + i];
+                    p_m = sc[26]; p_J1 = sc[28]; p_J3 = sc[29]; p_ctw = sc[31];
+                    if (MODE == 0) { p_d = sc[27]; p_ctf = sc[30]; }
                 }
                 k += 1;
                 if (k < a.n_steps) need_init = true;
@@ -439,28 +452,19 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 }
             }
         }
+#if QR_OPT_LOCKSTEP
+        // all warps of the CTA move through phase A and phase B together: the instruction working set at any
+        // time is one phase, fetched once for twelve warps
+        if (!__syncthreads_or(busy ? 1 : 0)) break;
+#else
         if (!__any_sync(FULL, busy)) break;
+#endif
         // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
         if (busy && need_init) {
             need_init = false;
-            EnvRegs<T> r;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) r.x[i] = x[i];
-            r.W3 = W3;
-            r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
-            if (c.goal_mode == 1) {   // goal from the pre-step state, main.py:145-147
-                const T Wv[3] = {y[12], y[13], W3};
-                T Rg[9], b1d[3], Wd[3];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Rg[i] = y[3 + i];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
-                ensure_so3<T>(Rg);   // get_desired -> state_decomposition
-                traj_wd<T>(Rg, Wv, b1d, Wd);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
-            }
-            T act[5];
+            // every load of this phase is issued before the first consumer (in-order issue: a stalled
+            // consumer would otherwise delay the independent loads behind it by a full memory round trip)
+            T act[5], b1d[3];
             bool act_f32 = a.act_f32 != 0;
             if (a.actions) {
                 const int64_t base = ((int64_t)k * N + e) * A;
@@ -478,7 +482,15 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 #pragma unroll
                     for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                 }
-            } else {
+            }
+            if (c.goal_mode == 1) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
+            }
+            // the observation at the end of this step reads xd, vd (goal rows 0-5): have them in L2 by then
+#pragma unroll
+            for (int i = 0; i < 6; ++i) prefetch_l2(a.goal + i * N + e);
+            if (!a.actions) {
                 const uint64_t gid = (uint64_t)(a.env_id_offset + e);
                 uint32_t rnd[8];
                 ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len, rnd);
@@ -487,16 +499,34 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 for (int i = 0; i < A; ++i) act[i] = (T)(2.0 * u01(rnd[i]) - 1.0);
                 act_f32 = false;
             }
+            EnvRegs<T> r;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) r.x[i] = x[i];
+            r.W3 = W3;
+            r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
+            if (c.goal_mode == 1) {   // goal from the pre-step state, main.py:145-147
+                const T Wv[3] = {y[12], y[13], W3};
+                T Rg[9], Wd[3];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rg[i] = y[3 + i];
+                ensure_so3<T>(Rg);   // get_desired -> state_decomposition
+                traj_wd<T>(Rg, Wv, b1d, Wd);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
+            }
             // observation_wrapper: SO(3) check of the incoming R (state_decomposition)
             int fl = ensure_so3<T>(y + 3);
 #pragma unroll
             for (int i = 0; i < 14; ++i) r.y[i] = y[i];
             T f, M[3];
             action_to_fM<T>(r, c, act, act_f32, f, M, MODE);
-            d.fm = f / p_m; d.g = c.g;
-            d.Mi0 = M[0] / p_J1; d.Mi1 = M[1] / p_J1;
-            d.kw0 = (p_J1 - p_J3) / p_J1; d.kw1 = (p_J3 - p_J1) / p_J1;
-            d.w3dot = M[2] / p_J3;
+            {
+                const T rm = (T)1 / p_m, rJ1 = (T)1 / p_J1, rJ3 = (T)1 / p_J3;   // inv(J) as the reference forms it (quad.py:329)
+                d.fm = f * rm; d.g = c.g;
+                d.Mi0 = M[0] * rJ1; d.Mi1 = M[1] * rJ1;
+                d.kw0 = (p_J1 - p_J3) * rJ1; d.kw1 = (p_J3 - p_J1) * rJ1;
+                d.w3dot = M[2] * rJ3;
+            }
             bool finite = true;
 #pragma unroll
             for (int i = 0; i < 3; ++i) finite = finite && (num<T>::abs(x[i]) <= num<T>::huge);

@@ -9,6 +9,9 @@
 #include <math.h>
 
 #define QR_DEV __device__ __forceinline__
+#ifndef QR_OPT_NEWTON
+#define QR_OPT_NEWTON 1
+#endif
 
 namespace qr {
 
@@ -62,7 +65,7 @@ template <typename T> QR_DEV T det3(const T* A)
 //   np.isclose(det R, 1, rtol=1e-5)              <=> |det - 1| <= 1e-8 + 1e-5
 // NaNs fail every comparison, exactly like numpy.  This runs inside EVERY right-hand-side evaluation
 // (state_decomposition, quad_utils.py:12-16), so it is written branch-free: one predicate at the end.
-template <typename T> QR_DEV bool so3_ok(const T* R)
+template <typename T> QR_DEV bool so3_ok(const T* R, T* defect = nullptr)
 {
     using N = num<T>;
     const T tol = (T)1e-5;
@@ -77,6 +80,7 @@ template <typename T> QR_DEV bool so3_ok(const T* R)
     T dt = N::abs(det3(R) - (T)1);
     // fmax drops NaNs, so test finiteness through a sum that propagates them
     T nanprobe = (d00 + d11 + d22) + (d01 + d02 + d12);
+    if (defect) *defect = (nanprobe == nanprobe) ? N::max(dg, od) : (T)1;   // max |RtR - I| (1 if not finite)
     return (dg <= tol + tol) && (od <= tol) && (dt <= (T)1e-8 + tol) && (nanprobe == nanprobe);
 }
 
@@ -148,10 +152,55 @@ template <typename T> __device__ __noinline__ int project_so3(T* R)
     return bad;
 }
 
-// ensure_SO3 on a register-resident R; flags: bit0 = projected, bit1 = projection failed
-template <typename T> QR_DEV int ensure_so3(T* R)
+// Polar factor of a NEAR-orthogonal matrix by Newton's iteration X <- (X + X^-T)/2 (Higham).  For det X > 0
+// the limit is U V^T, i.e. exactly what psvd + "U @ VT.T" returns (the sign correction is the identity);
+// convergence is quadratic, so an orthogonality defect of 1e-2 needs three steps to reach float64 rounding.
+// This is the common case (the Euler probe of select_initial_step leaves SO(3) by (h0 |W|)^2 ~ 1e-4..1e-2 in
+// ~12 % of env-steps); it stays in registers.  Returns false if the input is not in that regime.
+template <typename T> QR_DEV bool polar_newton(T* R)
 {
-    if (so3_ok(R)) return 0;
+    using N = num<T>;
+    T X[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) X[i] = R[i];
+    const int iters = (sizeof(T) == 8) ? 5 : 3;
+    T delta = 0;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        // cofactor matrix C (C_ij = d det / d X_ij); X^-T = C / det
+        T C[9];
+        // column-major: X[i + 3j] = X_ij ; C[i + 3j] = cofactor of X_ij
+        C[0] = X[4] * X[8] - X[7] * X[5]; C[3] = X[7] * X[2] - X[1] * X[8]; C[6] = X[1] * X[5] - X[4] * X[2];
+        C[1] = X[6] * X[5] - X[3] * X[8]; C[4] = X[0] * X[8] - X[6] * X[2]; C[7] = X[3] * X[2] - X[0] * X[5];
+        C[2] = X[3] * X[7] - X[6] * X[4]; C[5] = X[6] * X[1] - X[0] * X[7]; C[8] = X[0] * X[4] - X[3] * X[1];
+        const T det = X[0] * C[0] + X[1] * C[1] + X[2] * C[2];
+        if (!(det > (T)0.5)) return false;
+        const T hid = (T)0.5 / det;
+        delta = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const T xn = N::fma(C[i], hid, (T)0.5 * X[i]);
+            delta = N::max(delta, N::abs(xn - X[i]));
+            X[i] = xn;
+        }
+        if (delta <= ((sizeof(T) == 8) ? (T)1e-15 : (T)2e-7)) break;
+    }
+    if (!(delta <= ((sizeof(T) == 8) ? (T)1e-12 : (T)1e-5))) return false;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = X[i];
+    return true;
+}
+
+// ensure_SO3 on a register-resident R; flags: bit0 = projected, bit1 = projection failed
+// NEWTON: try the in-register Newton polar iteration first (used where the projection is expected to fire:
+// the Euler probe); everywhere else the rare projection goes straight to the out-of-line Jacobi routine.
+template <typename T, bool NEWTON = false> QR_DEV int ensure_so3(T* R)
+{
+    T defect;
+    if (so3_ok(R, &defect)) return 0;
+#if QR_OPT_NEWTON
+    if (NEWTON) { if (defect < (T)0.05 && polar_newton<T>(R)) return 1; }
+#endif
     T tmp[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) tmp[i] = R[i];
