@@ -45,10 +45,12 @@ template <typename T> struct EnvConst {
 // ---- Philox4x32-10 (Salmon et al., SC'11) ---------------------------------------------------------------
 struct Philox {
     uint32_t k0, k1;
+    // rolled on purpose: resets and in-kernel action draws sit in divergent, once-per-episode paths where
+    // code size (instruction cache) matters more than the ten-round latency
     QR_DEV void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) const
     {
         uint32_t a = k0, b = k1;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 10; ++r) {
             uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
             uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;

@@ -96,7 +96,7 @@ QR_DEV double warp_sum(double v)
 // (main.py:226-230).  Works through global memory so that the hot loop's registers are not affected; the
 // caller re-loads the env afterwards.  `o` receives the first observation of the new episode.
 template <typename T, int MODE>
-__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* dst1, float* dst2, T* scratch)
+__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* orow, T* scratch)
 {
     const StepArgs<T>& a = *ap;
     constexpr int O = (MODE == 1) ? 23 : 18;
@@ -134,10 +134,7 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
     scratch[26] = r.m; scratch[27] = r.d; scratch[28] = r.J1; scratch[29] = r.J3; scratch[30] = r.c_tf; scratch[31] = r.c_tw;
     store_params_goal(r, a, e, true, c.goal_mode == 1);
 #pragma unroll
-    for (int i = 0; i < O; ++i) {
-        if (dst1) dst1[i] = o[i];
-        if (dst2) dst2[i] = o[i];
-    }
+    for (int i = 0; i < O; ++i) orow[i] = o[i];   // replaces the terminal observation in the caller's tile row
 }
 
 QR_DEV float warp_sum_f(float v)
@@ -288,10 +285,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
                     }
                     ep_idx += 1;
-                    // the reset lane writes its own (new-episode) observation row; it is left out of the tile copy
-                    float* r1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (last ? a.obs + e * O : nullptr);
-                    float* r2 = (a.obs_roll && last) ? a.obs + e * O : nullptr;
-                    auto_reset_env<T, MODE>(&a, e, ep_idx, r1, r2, ks + lane * 32);   // the stage storage is free in phase A
+                    // the new episode's first observation replaces the terminal one in this lane's tile row
+                    auto_reset_env<T, MODE>(&a, e, ep_idx, os + lane * O, ks + lane * 32);   // the stage storage is free in phase A
                     ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
                     did_reset = true;
                 }
@@ -315,9 +310,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (mres) {   // once per episode
                     const int s_len = __reduce_add_sync(FULL, ep_len_done);
                     const unsigned mterm = __ballot_sync(FULL, did_reset && term);
-                    const double r0 = warp_sum(did_reset ? (double)ret_done0 : 0.0);
-                    const double r1 = warp_sum(did_reset ? (double)ret_done1 : 0.0);
-                    const double r0sq = warp_sum(did_reset ? (double)ret_done0 * (double)ret_done0 : 0.0);
+                    const double r0 = (double)warp_sum_f(did_reset ? (float)ret_done0 : 0.f);
+                    const double r1 = (double)warp_sum_f(did_reset ? (float)ret_done1 : 0.f);
+                    const double r0sq = (double)warp_sum_f(did_reset ? (float)ret_done0 * (float)ret_done0 : 0.f);
                     if (lane == 0) {
                         ws[0] += (double)__popc(mres); ws[3] += (double)s_len; ws[4] += (double)__popc(mterm);
                         ws[5] += (double)(__popc(mres) - __popc(mterm)); ws[1] += r0; ws[2] += r1; ws[6] += r0sq;
@@ -328,13 +323,13 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             // (32-env tile, sub-step); a group is written as O coalesced 128-byte stores through the
             // row -> lane map, rows that are not part of the group masked out.  Stragglers (lanes that
             // needed another attempt) belong to an older tile and are flushed in a further round.
-            unsigned rem = finmask & ~__ballot_sync(FULL, did_reset);
+            unsigned rem = finmask;
             const int myrow = (int)(e & 31);
             while (rem) {
                 const int lead = __ffs(rem) - 1;
                 const int64_t tb = __shfl_sync(FULL, e & ~(int64_t)31, lead);
                 const int kk = __shfl_sync(FULL, k, lead);
-                const bool mine = fin && !did_reset && ((e & ~(int64_t)31) == tb) && (k == kk);
+                const bool mine = fin && ((e & ~(int64_t)31) == tb) && (k == kk);
                 const unsigned grp = __ballot_sync(FULL, mine);
                 rem &= ~grp;
                 const bool lst = (kk == a.n_steps - 1);
