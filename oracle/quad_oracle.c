@@ -286,6 +286,52 @@ int qo_reset_from_uniforms_f64(const qo_config* c, int env_type, double udm_pct,
     return 0;
 }
 
+/* ---- trajectory generator, mode 0 (utils/trajectory_generator.py:113-173, 196-221) ------------------------ */
+
+/* Wd = [0, 0, b3 . (b1c x b1c_dot)] from the CURRENT state and the stored b1d (b1d_dot = 0 in mode 0):
+ * trajectory_generator.py:165-172.  get_desired first runs state_decomposition (ensure_SO3) on the state. */
+int qo_traj_wd_f64(int64_t n, const double* state, const double* b1d, double* Wd)
+{
+    for (int64_t e = 0; e < n; ++e) {
+        double R[9];
+        for (int i = 0; i < 9; ++i) R[i] = state[18 * e + 6 + i];
+        ensure_so3_f64(R, 0);
+        const double* W = state + 18 * e + 15;
+        const double* bd = b1d + 3 * e;
+        const double* b3 = R + 6;
+        double b3d[3];
+        for (int i = 0; i < 3; ++i) b3d[i] = R[i] * W[1] - R[i + 3] * W[0];      /* R hat(W) e3 */
+        double dp = fma(bd[2], b3[2], fma(bd[1], b3[1], bd[0] * b3[0]));
+        double dq = fma(bd[2], b3d[2], fma(bd[1], b3d[1], bd[0] * b3d[0]));
+        double b1c[3], b1cd[3];
+        for (int i = 0; i < 3; ++i) {
+            b1c[i] = bd[i] - dp * b3[i];
+            b1cd[i] = 0.0 - ((0.0 * b3[i] + dq * b3[i]) + dp * b3d[i]);
+        }
+        double oc0 = b1c[1] * b1cd[2] - b1c[2] * b1cd[1];
+        double oc1 = b1c[2] * b1cd[0] - b1c[0] * b1cd[2];
+        double oc2 = b1c[0] * b1cd[1] - b1c[1] * b1cd[0];
+        Wd[3 * e] = 0; Wd[3 * e + 1] = 0;
+        Wd[3 * e + 2] = fma(b3[2], oc2, fma(b3[1], oc1, b3[0] * oc0));
+    }
+    return 0;
+}
+
+/* mark_traj_start + first get_desired(mode 0) (main.py:226-229): b1d = Rz(theta) [cos psi, sin psi, 0] with psi the
+ * heading of b1 of the (float32-cast) reset state; theta is the caller's draw of U(-25 deg, 25 deg). */
+int qo_traj_init_mode0_f64(int64_t n, const double* state, const double* theta, double* b1d)
+{
+    for (int64_t e = 0; e < n; ++e) {
+        double R[9];
+        for (int i = 0; i < 9; ++i) R[i] = (double)(float)state[18 * e + 6 + i];
+        ensure_so3_f64(R, 0);
+        double psi = atan2(R[1], R[0]);
+        double cps = cos(psi), sps = sin(psi), cth = cos(theta[e]), sth = sin(theta[e]);
+        b1d[3 * e] = cth * cps - sth * sps; b1d[3 * e + 1] = sth * cps + cth * sps; b1d[3 * e + 2] = 0.0;
+    }
+    return 0;
+}
+
 /* ---- Philox4x32-10 ----------------------------------------------------------------------------------- */
 
 void qo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])

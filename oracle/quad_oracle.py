@@ -59,6 +59,8 @@ def lib():
         L.qo_ensure_so3_f64.argtypes = [C.c_int64, dp]
         L.qo_ensure_so3_f64.restype = C.c_int64
         L.qo_reset_from_uniforms_f64.argtypes = [C.POINTER(QoConfig), C.c_int, C.c_double, C.c_int64, dp, dp, dp, dp]
+        L.qo_traj_wd_f64.argtypes = [C.c_int64, dp, dp, dp]
+        L.qo_traj_init_mode0_f64.argtypes = [C.c_int64, dp, dp, dp]
         L.qo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.qo_set_threads.argtypes = [C.c_int]
         L.qo_get_max_threads.restype = C.c_int
@@ -155,6 +157,21 @@ def ensure_so3(R):
     R = np.array(R, dtype=np.float64, order="C", copy=True)
     k = lib().qo_ensure_so3_f64(R.shape[0], _p(R, C.c_double))
     return R, int(k)
+
+
+def traj_wd(state, b1d):
+    """Mode-0 goal generator: Wd[n,3] from the current state and the stored heading goal."""
+    state = np.ascontiguousarray(state, np.float64); b1d = np.ascontiguousarray(b1d, np.float64)
+    out = np.empty((state.shape[0], 3))
+    lib().qo_traj_wd_f64(state.shape[0], _p(state, C.c_double), _p(b1d, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def traj_init_mode0(state, theta):
+    state = np.ascontiguousarray(state, np.float64); theta = np.ascontiguousarray(theta, np.float64)
+    out = np.empty((state.shape[0], 3))
+    lib().qo_traj_init_mode0_f64(state.shape[0], _p(state, C.c_double), _p(theta, C.c_double), _p(out, C.c_double))
+    return out
 
 
 def philox4x32_10(ctr, key):

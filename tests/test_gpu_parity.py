@@ -232,8 +232,7 @@ def test_goal_mode0_matches_reference_trajgen():
     env.set_state(g["state_in"], g["integ_in"], g["params"], goal_in)
     obs, rew, done, _, _ = env.step(_t(g["action"], torch.float64))
     st, ig, _, gl = env.get_state()
-    # rows that start an episode used a goal computed from the float32 reset state (main.py:226-229)
-    ok = ~g["episode_start"]
+    ok = np.ones(n, bool)
     assert np.abs(gl[ok, 9:12] - g["goal"][ok, 9:12]).max() <= 1e-12
     assert _relerr(st[ok], g["state_out"][ok]) <= 1e-12
     o = obs[0].cpu().numpy()
@@ -316,3 +315,76 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_native, "LIB_PATH", "/nonexistent/libquadrotor_b200.so")
     with pytest.raises(_native.NativeError):
         _native.load()
+
+
+def test_init_goal_matches_oracle_trajgen():
+    """qr_init_goal == mark_traj_start + get_desired(mode 0) on the float32-cast reset state (main.py:226-229),
+    with theta taken from the env's Philox stream (uniform #19 of the episode)."""
+    n, seed = 256, 5
+    env = _env(n, "MONO", seed=seed, goal_mode="traj0")
+    env.reset(); env.init_goal()
+    st, _, _, gl = env.get_state()
+    u = _philox_uniforms(seed, list(range(n)), 1)
+    theta = np.deg2rad(-25.0 + 50.0 * u[:, 19])
+    st32 = st.astype(np.float32).astype(np.float64)
+    b1d = qo.traj_init_mode0(st32, theta)
+    assert np.abs(gl[:, 6:9] - b1d).max() <= 1e-14
+    assert np.abs(gl[:, 9:12] - qo.traj_wd(st32, b1d)).max() <= 1e-13
+    assert np.abs(gl[:, 0:6]).max() == 0
+    env.close()
+
+
+def test_fp32_reset_is_a_valid_state():
+    n = 4096
+    env = _env(n, "MODUL", torch.float32, seed=9)
+    env.reset()
+    st, ig, par, _ = env.get_state()
+    R = st[:, 6:15].reshape(n, 3, 3).transpose(0, 2, 1)
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 5e-6 and np.abs(np.linalg.det(R) - 1).max() < 5e-6
+    assert np.abs(st[:, 0:3]).max() <= 0.6 + 1e-6 and np.abs(st[:, 3:6]).max() <= 2.0 + 1e-6
+    assert np.abs(st[:, 15:18]).max() <= np.pi + 1e-5 and (ig == 0).all()
+    still = np.abs(st[:, 0:6]).sum(axis=1) == 0
+    assert 0.15 < still.mean() < 0.25                      # 20 % spawn at the origin (quad.py:342)
+    assert np.abs(par[:, 0] - 2.15).max() <= 0.2151 and par[:, 0].std() > 0.05
+    env.close()
+
+
+def test_vector_env_facade():
+    from gym_rotor_b200 import vec_env
+    n = 2048
+    ve = vec_env.QuadVectorEnv(n, framework="MODUL", max_episode_steps=30, dtype=torch.float32, seed=1)
+    obs, info = ve.reset()
+    assert obs[0].shape == (n, 15) and obs[1].shape == (n, 3) and obs[0].dtype == torch.float32
+    g = torch.Generator(device="cuda:0"); g.manual_seed(0)
+    n_trunc = n_term = 0
+    for t in range(40):
+        a = torch.rand((n, 5), device="cuda:0", generator=g) * 2 - 1
+        obs, rew, term, trunc, info = ve.step(a)
+        assert rew.shape == (n, 2) and term.shape == (n,) and trunc.shape == (n,)
+        assert torch.isfinite(obs[0]).all() and torch.isfinite(rew).all()
+        assert ((rew >= 0) & (rew <= 1) | (rew == -1)).all()
+        n_trunc += int(trunc.sum()); n_term += int(term.sum())
+        # a finished env already shows the first observation of its next episode: integral terms restart near 0
+        fin = term | trunc
+        if fin.any():
+            assert obs[0][fin, 3:6].abs().max() < 0.01
+    s = ve.env.stats()
+    assert n_trunc > 0 and n_term > 0 and s[0] == n_term + int(s[5]) and s[7] == 40 * n
+    assert abs(s[10:14].sum() - s[7]) < 0.5
+    ve.close()
+
+
+def test_status_flags_nonfinite_state():
+    """scipy raises on a non-finite y0; the kernel flags the env instead and leaves the others untouched."""
+    n = 64
+    rng = np.random.default_rng(0)
+    st, ig, par = qo.COracle("MONO").reset_from_uniforms(rng.random((n, 20)))
+    st[5, 2] = np.nan
+    goal = np.zeros((n, 12)); goal[:, 6] = 1.0
+    env = _env(n, "MONO")
+    env.set_state(st, ig, par, goal)
+    env.step(_t(rng.uniform(-1, 1, (n, 4)), torch.float64))
+    status = env.status.cpu().numpy()
+    assert status[5] & 1 and (np.delete(status, 5) == 0).all()
+    assert np.isfinite(np.delete(env.get_state()[0], 5, axis=0)).all()
+    env.close()

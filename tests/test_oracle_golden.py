@@ -154,3 +154,23 @@ def test_philox_known_answer():
     assert qo.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert qo.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_trajgen_mode0_matches_reference():
+    """Goal generator mode 0: Wd from the pre-step state equals what the reference's TrajectoryGenerator produced
+    (trajectory_generator.py:165-172); b1d stays a unit heading vector in the horizontal plane."""
+    g = _load("step_mono_a64.npz")
+    ok = ~g["episode_start"]
+    # every recorded goal was produced by get_desired(env.get_current_state()) right before the step (main.py:145-147)
+    wd = qo.traj_wd(g["state_in"], g["goal"][:, 6:9])
+    assert np.abs(wd - g["goal"][:, 9:12]).max() < 1e-13
+    assert np.abs(g["goal"][:, 0:6]).max() == 0 and np.abs(g["goal"][:, 8]).max() == 0
+    # the heading goal was fixed at trajectory start from the FLOAT32 reset state (main.py:226-229):
+    # Rz(theta) applied to the current heading, |theta| <= 25 deg
+    st32 = g["reset_state32"][~ok].astype(np.float64)
+    b1d0 = qo.traj_init_mode0(st32, np.zeros(len(st32)))
+    ang = np.arctan2(g["goal"][~ok, 7], g["goal"][~ok, 6]) - np.arctan2(b1d0[:, 1], b1d0[:, 0])
+    ang = (ang + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(ang).max() <= np.deg2rad(25) + 1e-12
+    b1d_again = qo.traj_init_mode0(st32, ang)
+    assert np.abs(b1d_again - g["goal"][~ok, 6:9]).max() < 1e-12
