@@ -352,12 +352,12 @@ def test_fp32_reset_is_a_valid_state():
 def test_vector_env_facade():
     from gym_rotor_b200 import vec_env
     n = 2048
-    ve = vec_env.QuadVectorEnv(n, framework="MODUL", max_episode_steps=30, dtype=torch.float32, seed=1)
+    ve = vec_env.QuadVectorEnv(n, framework="MODUL", max_episode_steps=90, dtype=torch.float32, seed=1)
     obs, info = ve.reset()
     assert obs[0].shape == (n, 15) and obs[1].shape == (n, 3) and obs[0].dtype == torch.float32
     g = torch.Generator(device="cuda:0"); g.manual_seed(0)
     n_trunc = n_term = 0
-    for t in range(40):
+    for t in range(120):
         a = torch.rand((n, 5), device="cuda:0", generator=g) * 2 - 1
         obs, rew, term, trunc, info = ve.step(a)
         assert rew.shape == (n, 2) and term.shape == (n,) and trunc.shape == (n,)
@@ -369,7 +369,7 @@ def test_vector_env_facade():
         if fin.any():
             assert obs[0][fin, 3:6].abs().max() < 0.01
     s = ve.env.stats()
-    assert n_trunc > 0 and n_term > 0 and s[0] == n_term + int(s[5]) and s[7] == 40 * n
+    assert n_trunc > 0 and n_term > 0 and s[0] == n_term + int(s[5]) and s[7] == 120 * n
     assert abs(s[10:14].sum() - s[7]) < 0.5
     ve.close()
 
