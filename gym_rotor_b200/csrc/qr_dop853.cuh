@@ -168,13 +168,16 @@ template <typename T> struct Dyn {
 };
 
 // One right-hand-side evaluation at stage point (ys, W3s) -> k[14].  Returns ensure_SO3 flags.
-template <typename T, bool NEWTON = false> QR_DEV int rhs14(const T* ys, T W3s, const Dyn<T>& d, T* k)
+// CHECK = false: the caller has just run ensure_SO3 on this very matrix (it passed, or it was re-projected and
+// passes now), so the reference's test inside this evaluation is known to succeed and is not repeated.
+template <typename T, bool NEWTON = false, bool CHECK = true> QR_DEV int rhs14(const T* ys, T W3s, const Dyn<T>& d, T* k)
 {
     using N = num<T>;
     T R[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = ys[3 + i];
-    int fl = ensure_so3<T, NEWTON>(R);  // state_decomposition -> ensure_SO3 on every call (quad_utils.py:12-16)
+    int fl = 0;
+    if (CHECK) fl = ensure_so3<T, NEWTON>(R);  // state_decomposition -> ensure_SO3 on every call (quad_utils.py:12-16)
     const T W0 = ys[12], W1 = ys[13], W2 = W3s;
     // v' = g e3 - (f/m) R e3
     k[0] = -d.fm * R[6];
@@ -209,7 +212,7 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
 {
     using N = num<T>;
     o.t = 0; o.rejected = 0; o.nfev = 2; o.status = 0; o.nproj = 0;
-    int fl = rhs14<T>(y, W3, d, K0);
+    int fl = rhs14<T, false, false>(y, W3, d, K0);   // y's R was SO(3)-checked by the caller (observation_wrapper)
     o.nproj += fl & 1; if (fl & 2) o.status |= 4;
     T s0 = 0, s1 = 0;   // sums of (y/sc)^2 and (f0/sc)^2 over all 18 components
     T isc[14], iscx[3];
@@ -261,7 +264,7 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
     h_abs = (h1 < h_abs) ? h1 : h_abs;
     h_abs = (Tend < h_abs) ? Tend : h_abs;
     // first _step_impl: h_abs is raised to min_step = 10 ulp(t) if smaller
-    const T min_step = (T)10 * N::abs(N::nextafter((T)0, N::inf()) - (T)0);
+    const T min_step = (T)10 * N::ulp_up((T)0);
     o.h_abs = (h_abs < min_step) ? min_step : h_abs;
 }
 
@@ -279,7 +282,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
 {
     using N = num<T>;
     using TB = tab<T>;
-    const T min_step = (T)10 * N::abs(N::nextafter(o.t, N::inf()) - o.t);
+    const T min_step = (T)10 * N::ulp_up(o.t);
     const bool too_small = o.h_abs < min_step;   // TOO_SMALL_STEP: keep the last accepted y
     T t_new = o.t + o.h_abs;
     if (t_new - Tend > (T)0) t_new = Tend;
@@ -412,7 +415,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         o.nproj += fl & 1; if (fl & 2) o.status |= 4;
         // next _step_impl call: fresh rejection flag, h_abs raised to min_step(t) if smaller
         o.rejected = 0;
-        const T ms = (T)10 * N::abs(N::nextafter(o.t, N::inf()) - o.t);
+        const T ms = (T)10 * N::ulp_up(o.t);
         if (o.h_abs < ms) o.h_abs = ms;
         return false;
     }

@@ -251,10 +251,17 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
 // ---- reward and termination on the float32 observation --------------------------------------------------------
 // numpy: norm(v,2) of a float32 3-vector = sqrtf(float(double-accumulated float32 products)) (OpenBLAS sdot);
 // `**2` restated as a correctly rounded square (numpy's powf(x,2) differs by 1 ulp in ~0.07 % of cases).
-QR_DEV float norm2sq_f32(const float* v)
+// EXACT = float64 (parity) mode.  In float32 mode the observation already differs from numpy's at rounding
+// level, so the float64 accumulation (three conversions through the FP64 pipe) is replaced by a float32 sum.
+template <bool EXACT> QR_DEV float norm2sq_f32(const float* v)
 {
-    double s = (double)__fmul_rn(v[0], v[0]) + (double)__fmul_rn(v[1], v[1]) + (double)__fmul_rn(v[2], v[2]);
-    float n = __fsqrt_rn((float)s);
+    float n;
+    if (EXACT) {
+        double s = (double)__fmul_rn(v[0], v[0]) + (double)__fmul_rn(v[1], v[1]) + (double)__fmul_rn(v[2], v[2]);
+        n = __fsqrt_rn((float)s);
+    } else {
+        n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+    }
     return __fmul_rn(n, n);
 }
 QR_DEV double interp01(double r, double rmin, double slope)
@@ -270,8 +277,8 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
 {
     dn[0] = 0; dn[1] = 0;
     if (mode == 1) {
-        float rx = __fmul_rn(c.nCx, norm2sq_f32(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32(o + 3));
-        float rv = __fmul_rn(c.nCv, norm2sq_f32(o + 6)), rw = __fmul_rn(c.nCW, norm2sq_f32(o + 20));
+        float rx = __fmul_rn(c.nCx, norm2sq_f32<sizeof(T) == 8>(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32<sizeof(T) == 8>(o + 3));
+        float rv = __fmul_rn(c.nCv, norm2sq_f32<sizeof(T) == 8>(o + 6)), rw = __fmul_rn(c.nCW, norm2sq_f32<sizeof(T) == 8>(o + 20));
         float a18 = fabsf(o[18]), a19 = fabsf(o[19]);
         float rb = __fmul_rn(c.nCb1, a18), rib = __fmul_rn(c.nCIb1, __fmul_rn(a19, a19));
         float r = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(rx, rix), rv), rb), rib), rw);
@@ -281,8 +288,8 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
         rew[0] = dn[0] ? -1.0 : interp01((double)r, c.rmin, c.slope);
         rew[1] = 0.0;
     } else {
-        float rx = __fmul_rn(c.nCx, norm2sq_f32(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32(o + 3));
-        float rv = __fmul_rn(c.nCv, norm2sq_f32(o + 6)), rw = __fmul_rn(c.nCw12, norm2sq_f32(o + 12));
+        float rx = __fmul_rn(c.nCx, norm2sq_f32<sizeof(T) == 8>(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32<sizeof(T) == 8>(o + 3));
+        float rv = __fmul_rn(c.nCv, norm2sq_f32<sizeof(T) == 8>(o + 6)), rw = __fmul_rn(c.nCw12, norm2sq_f32<sizeof(T) == 8>(o + 12));
         float r1 = __fadd_rn(__fadd_rn(__fadd_rn(rx, rix), rv), rw);
         float a0 = fabsf(o[15]), a1 = fabsf(o[16]), a2 = fabsf(o[17]);
         float r2 = __fadd_rn(__fadd_rn(__fmul_rn(c.nCb1, a0), __fmul_rn(c.nCIb1, __fmul_rn(a1, a1))),

@@ -494,25 +494,23 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 for (int i = 0; i < A; ++i) act[i] = (T)(2.0 * u01(rnd[i]) - 1.0);
                 act_f32 = false;
             }
+            // state_decomposition of the incoming state: get_desired (trajectory_generator.py:115) and
+            // observation_wrapper (coupled:58) both run ensure_SO3 on the same R; once is enough
+            int fl = ensure_so3<T>(y + 3);
             EnvRegs<T> r;
 #pragma unroll
             for (int i = 0; i < 3; ++i) r.x[i] = x[i];
+#pragma unroll
+            for (int i = 0; i < 14; ++i) r.y[i] = y[i];
             r.W3 = W3;
             r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
             if (c.goal_mode == 1) {   // goal from the pre-step state, main.py:145-147
                 const T Wv[3] = {y[12], y[13], W3};
-                T Rg[9], Wd[3];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Rg[i] = y[3 + i];
-                ensure_so3<T>(Rg);   // get_desired -> state_decomposition
-                traj_wd<T>(Rg, Wv, b1d, Wd);
+                T Wd[3];
+                traj_wd<T>(y + 3, Wv, b1d, Wd);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
             }
-            // observation_wrapper: SO(3) check of the incoming R (state_decomposition)
-            int fl = ensure_so3<T>(y + 3);
-#pragma unroll
-            for (int i = 0; i < 14; ++i) r.y[i] = y[i];
             T f, M[3];
             action_to_fM<T>(r, c, act, act_f32, f, M, MODE);
             {

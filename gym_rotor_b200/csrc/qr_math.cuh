@@ -26,6 +26,8 @@ template <> struct num<float> {
     static QR_DEV float min(float a, float b) { return fminf(a, b); }
     static QR_DEV float atan2(float a, float b) { return atan2f(a, b); }
     static QR_DEV float nextafter(float a, float b) { return nextafterf(a, b); }
+    // spacing of the floats above t (t >= 0, finite): what scipy takes as |nextafter(t, inf) - t|
+    static QR_DEV float ulp_up(float t) { return __int_as_float(__float_as_int(t) + 1) - t; }
     static QR_DEV float inf() { return __int_as_float(0x7f800000); }
     // x^(1/8) and x^(-1/8) by square-root chains: <= 2 ulp, no transcendental (only scales the step size)
     static QR_DEV float asqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -46,6 +48,7 @@ template <> struct num<double> {
     static QR_DEV double min(double a, double b) { return fmin(a, b); }
     static QR_DEV double atan2(double a, double b) { return ::atan2(a, b); }
     static QR_DEV double nextafter(double a, double b) { return ::nextafter(a, b); }
+    static QR_DEV double ulp_up(double t) { return __longlong_as_double(__double_as_longlong(t) + 1) - t; }
     static QR_DEV double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static QR_DEV double root8(double x) { return ::sqrt(::sqrt(::sqrt(x))); }
     static QR_DEV double inv_root8(double x) { return 1.0 / ::sqrt(::sqrt(::sqrt(x))); }
