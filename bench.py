@@ -28,6 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 ALG_BYTES = {"MONO_f32": 366, "MONO_f64": 614, "MODUL_f32": 363}   # SURVEY 8(d), per env-step
 ALG_FLOPS = 5450                                                   # SURVEY 8(d), one DOP853 attempt
 STATS_EVERY = 128
+DRAM_BYTES_PER_ENV_STEP_NCU = 417.3   # ncu --set full capture r01k: 875.2 MB per launch of 2^21 env-steps
 
 
 def _peaks():
@@ -195,6 +196,7 @@ def run_ours(args):
             return allreduce_stats(env, dev) if world > 1 else env.stats()
         return None
 
+    sampler = ClockSampler(local); sampler.start()   # samples under load: warm-up + timed region
     for i in range(args.warmup):
         one_step(i)
     env.stats()
@@ -202,7 +204,6 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local); sampler.start()
     launches0 = env.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -276,7 +277,9 @@ def run_ours(args):
                     "steps": e2e_steps, "api": "qr_step_host (pinned host actions in; obs, reward, done out)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": which, "kernel": "qr::k_step<%s>" % ("double" if args.dtype == "f64" else "float"),
+                         "traffic": (DRAM_BYTES_PER_ENV_STEP_NCU * n * fused / 1e9) if (fw == "MONO" and args.dtype == "f32") else None,
+                         "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01k_kstep_f32_ncu_digest.txt)",
+                         "peak_source": which, "kernel": "qr::k_step<%s>" % ("double" if args.dtype == "f64" else "float"),
                          "algorithmic_bytes_per_env_step": bytes_per, "kernel_ms": kernel_ms},
             "roofline_fp": {"bound": "fp%s issue" % ("64" if args.dtype == "f64" else "32"),
                             "achieved": ALG_FLOPS * mean_att * per_gpu_steps / 1e12, "peak": fp_peak, "unit": "TFLOP/s",
