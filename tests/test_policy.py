@@ -1,0 +1,59 @@
+"""Effective-weight actor inference: the extracted maps reproduce the reference actors' outputs,
+and on the GPU the policy-in-the-loop episode reproduces the reference's own evaluation run (KAT-2)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("tag,agents", [("mono", 1), ("modul", 2)])
+def test_effective_actor_matches_reference_outputs(tag, agents):
+    from gym_rotor_b200.policy import EffectiveActor
+    z = np.load(os.path.join(G, "policy_td3_%s.npz" % tag))
+    for i in range(agents):
+        pi = EffectiveActor(z, agent=i, device="cpu")
+        act = pi(torch.as_tensor(z["a%d_obs" % i])).numpy()
+        ref = z["a%d_act" % i]
+        assert act.shape == ref.shape
+        # float32 forward in a different operation order; the yaw actor has pre-activations of magnitude ~6
+        assert np.abs(act - ref).max() < 1e-4, (tag, i, np.abs(act - ref).max())
+        assert np.abs(ref).max() <= 1.0 and ref.std() > 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fw,tag,A", [("MONO", "mono", [4]), ("MODUL", "modul", [4, 1])])
+def test_policy_in_the_loop_reproduces_reference_eval_episode(fw, tag, A):
+    """BASELINE config 5 at N=1 scale: fp64 env on the GPU + the extracted actor, 1000 steps, against the episode the
+    reference flew with the same checkpoint (return 989.8 MONO; 992.6 / 998.0 MODUL)."""
+    from gym_rotor_b200 import vec_env
+    from gym_rotor_b200.policy import EffectiveActor
+    ep = np.load(os.path.join(G, "eval_%s.npz" % tag))
+    z = np.load(os.path.join(G, "policy_td3_%s.npz" % tag))
+    pis = [EffectiveActor(z, agent=i) for i in range(len(A))]
+    n = 4     # four identical copies: also checks that envs do not interact
+    env = vec_env.BatchedQuadEnv(n, framework=fw, dtype=torch.float64, goal_mode="traj0")
+    env.set_state(np.tile(ep["state0"], (n, 1)), np.tile(ep["integ0"], (n, 1)), np.tile(ep["params"], (n, 1)),
+                  np.tile(ep["goal0"], (n, 1)))
+    obs = torch.as_tensor(np.tile(ep["obs0"], (n, 1)), device="cuda:0")
+    ret = np.zeros(len(A))
+    H = len(ep["reward"])
+    worst_a = worst_s = 0.0
+    for t in range(H):
+        parts = [obs[:, :15], obs[:, 15:18]] if fw == "MODUL" else [obs]
+        act = torch.cat([pi(o) for pi, o in zip(pis, parts)], dim=1).to(torch.float64)
+        worst_a = max(worst_a, float((act[0].cpu() - torch.as_tensor(ep["action"][t])).abs().max()))
+        o_n, rew, done, _, _ = env.step(act)
+        obs = torch.cat(o_n, dim=1)
+        ret += rew[0].cpu().numpy()
+        assert not bool(done.any())
+        if t % 100 == 99:
+            worst_s = max(worst_s, float(np.abs(env.get_state()[0][0] - ep["state"][t]).max()))
+    st = env.get_state()[0]
+    assert np.abs(st - st[0]).max() == 0.0                     # identical envs stay identical
+    assert worst_a < 1e-3 and worst_s < 1e-3, (worst_a, worst_s)
+    assert np.abs(ret - ep["reward"].sum(axis=0)).max() < 0.05, (ret, ep["reward"].sum(axis=0))
+    assert ret[0] > 985
+    env.close()
