@@ -170,9 +170,10 @@ def run_ours(args):
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     n = args.envs_per_gpu
     env = vec_env.BatchedQuadEnv(n, framework=fw, dtype=dtype, device=dev, seed=args.seed, autoreset=True,
-                                 goal_mode="traj0" if fw != "QUAD" else "external", env_type="train", max_episode_steps=4000,
+                                 goal_mode="traj0" if fw != "QUAD" else "external",
+                                 env_type="eval" if args.policy else "train", max_episode_steps=1000 if args.policy else 4000,
                                  env_id_offset=rank * n, diagnostics=False)
-    env.reset()
+    env.reset(env_type="eval" if args.policy else "train")
     if fw != "QUAD":
         env.init_goal()
     env.get_norm_error_state()
@@ -186,9 +187,14 @@ def run_ours(args):
         pool = [torch.rand((n, A), device=dev, dtype=torch.float32, generator=gen) * 2 - 1 for _ in range(4)]
     stats_total = np.zeros(16)
     fused = max(1, args.fused)
+    actors = None
+    if args.policy:   # BASELINE config 5: the reference's shipped TD3 actor in the loop (obs -> action on device)
+        actors = torch.empty((n, env.act_dim), dtype=torch.float32, device=dev)   # action buffer of qr_policy_td3
 
     def one_step(i):
-        if fused > 1:
+        if actors is not None:
+            env.step(env.policy_td3(out=actors))   # compiled actor kernel + step kernel: two launches per env.step
+        elif fused > 1:
             env.rollout(fused)      # `fused` env.step() calls in one launch, Philox actions drawn in-kernel
         else:
             env.step(pool[i % len(pool)])
@@ -268,7 +274,8 @@ def run_ours(args):
                                    "on-device trajgen mode-0 goals, in-kernel auto reset (4000-step limit), "
                                    "stats all-reduce every %d steps" % (
                                        {"MONO": "CoupledWrapper", "MODUL": "DecoupledWrapper", "QUAD": "Quad-v0"}[fw], n, STATS_EVERY),
-                       "envs_per_gpu": n, "framework": fw, "actions": args.actions, "fused_steps_per_launch": fused,
+                       "envs_per_gpu": n, "framework": fw, "actions": ("shipped TD3 actor in the loop (qr_policy_td3, compiled effective weights)" if args.policy else args.actions),
+                       "fused_steps_per_launch": fused,
                        "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2)" % (bytes_per * n / 1e6),
                        "mean_dop853_attempts": mean_att, "episodes": stats_total[0],
                        "mean_episode_length": float(stats_total[3] / max(1.0, stats_total[0]))},
@@ -311,6 +318,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--actions", default="random", choices=["random", "zero"])
+    ap.add_argument("--policy", action="store_true", help="config 5: the shipped TD3 actor in the loop")
     ap.add_argument("--fused", type=int, default=1, help="env.step() calls fused per launch (qr_rollout, in-kernel actions)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -23,7 +23,7 @@ STAT_NAMES = ["episodes", "return0", "return1", "length", "crashed", "truncated"
 
 # every symbol include/quadrotor_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = ["qr_default_config", "qr_create", "qr_destroy", "qr_get_config", "qr_get_buffers", "qr_reset",
-           "qr_init_goal", "qr_norm_error_state", "qr_step", "qr_rollout", "qr_step_host", "qr_set_state_host",
+           "qr_init_goal", "qr_norm_error_state", "qr_policy_td3", "qr_step", "qr_rollout", "qr_step_host", "qr_set_state_host",
            "qr_get_state_host", "qr_stats", "qr_launch_count", "qr_last_error", "qr_abi_version"]
 
 
@@ -72,6 +72,7 @@ def load():
     L.qr_reset.argtypes = [vp, u8p, C.c_int, vp]
     L.qr_init_goal.argtypes = [vp, u8p, vp]
     L.qr_norm_error_state.argtypes = [vp, u8p, vp]
+    L.qr_policy_td3.argtypes = [vp, vp, vp]
     L.qr_step.argtypes = [vp, vp, C.c_int, vp]
     L.qr_rollout.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
     L.qr_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp]

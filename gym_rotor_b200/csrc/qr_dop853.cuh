@@ -28,10 +28,6 @@
 #include "qr_math.cuh"
 #include "dop853_tableau.h"
 
-#ifndef QR_OPT_PAIR2
-#define QR_OPT_PAIR2 0
-#endif
-
 namespace qr {
 
 // ---- tableau in constant memory (uniform-indexed loads in the rolled stage loop) ------------------------
@@ -132,15 +128,11 @@ template <typename T> QR_DEV void ks_store_lane(T* col, int lane, const T* k)
 
 // acc[0..13] += c * k[0..13].  float32 on sm_100a: seven packed FFMA2 (fma.rn.f32x2) instead of fourteen FFMA --
 // the kernel is issue bound, not FMA-pipe bound, so halving the instruction count of the stage sums pays.
-#ifndef QR_OPT_FFMA2
-#define QR_OPT_FFMA2 1
-#endif
 template <typename T> QR_DEV void axpy14(T c, const T* k, T* acc)
 {
 #pragma unroll
     for (int i = 0; i < 14; ++i) acc[i] = num<T>::fma(c, k[i], acc[i]);
 }
-#if QR_OPT_FFMA2
 template <> QR_DEV void axpy14<float>(float c, const float* k, float* acc)
 {
     const float2 cc = make_float2(c, c);
@@ -150,7 +142,6 @@ template <> QR_DEV void axpy14<float>(float c, const float* k, float* acc)
         acc[2 * i] = r.x; acc[2 * i + 1] = r.y;
     }
 }
-#endif
 // three weighted sums at once (y_new and the two error estimators)
 template <typename T> QR_DEV void axpy14x3(T b, T e5, T e3, const T* k, T* sb, T* s5, T* s3)
 {
@@ -306,47 +297,15 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
             axpy14<T>(ha0, K0, ys);
         }
         const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
-        int j = jlo;
-#if QR_OPT_PAIR2 == 2
-        // software pipelined: the next K vector is in flight while the current one is accumulated
-        if (j < s) {
-            T ka[14], kb[14];
-            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, ka);
-            T ca = h * TB::A(s, j);
+        // (measured and dropped: two K vectors per trip / software pipelining -- the extra registers cost more
+        //  than the exposed LDS latency, profiles/r01_summary.md)
 #pragma unroll 1
-            for (; j < s; j += 2) {
-                const bool has_b = j + 1 < s;
-                T cb = 0;
-                if (has_b) { ks_load_lane<T>(kl + k_slot(j + 1) * QR_SLOT_ELEMS, lane, kb); cb = h * TB::A(s, j + 1); }
-                axpy14<T>(ca, ka, ys);
-                if (j + 2 < s) { ks_load_lane<T>(kl + k_slot(j + 2) * QR_SLOT_ELEMS, lane, ka); ca = h * TB::A(s, j + 2); }
-                if (has_b) axpy14<T>(cb, kb, ys);
-            }
-        }
-#elif QR_OPT_PAIR2 == 1
-#pragma unroll 1
-        for (; j + 1 < s; j += 2) {   // two K vectors in flight per trip
-            const T c0 = h * TB::A(s, j), c1 = h * TB::A(s, j + 1);
-            T k0[14], k1[14];
-            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k0);
-            ks_load_lane<T>(kl + k_slot(j + 1) * QR_SLOT_ELEMS, lane, k1);
-            axpy14<T>(c0, k0, ys); axpy14<T>(c1, k1, ys);
-        }
-        if (j < s) {
+        for (int j = jlo; j < s; ++j) {
             const T c = h * TB::A(s, j);
             T k[14];
             ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k);
             axpy14<T>(c, k, ys);
         }
-#else
-#pragma unroll 1
-        for (; j < s; ++j) {
-            const T c = h * TB::A(s, j);
-            T k[14];
-            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k);
-            axpy14<T>(c, k, ys);
-        }
-#endif
         const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
         if (s >= 5) {
             const T bs = TB::B(s), e5s = TB::E5(s), e3s = TB::E3(s);

@@ -1,22 +1,17 @@
 // qr_kernels.cuh -- the fused env.step() kernel and its small companions (reset, goal init, observation).
 //
-// One env per thread, structure-of-arrays state ([component][env], coalesced), state resident in registers
-// across `n_steps` fused sub-steps, float32 observations staged through shared memory so that the
-// row-major [N][O] output is written as full 128-byte lines.  No tensor cores: the dynamics are not a
-// dense contraction; the roofline that binds is FP32/FP64 issue.
+// Step kernel: persistent warps, one env per lane, structure-of-arrays state ([component][env], coalesced),
+// state resident in registers across `n_steps` fused sub-steps, DOP853 stage derivatives in shared memory,
+// float32 observations staged through a per-warp shared tile so that the row-major [N][O] output leaves as
+// full 128-byte lines.  No tensor cores: the dynamics are not a dense contraction; the roofline that binds is
+// FP32/FP64 instruction issue.
 //
 // Replaces QuadEnv.step (gym_rotor/envs/quad.py:142-168) with its wrappers' overrides
 // (coupled_yaw_wrapper.py:44-110, decoupled_yaw_wrapper.py:49-161) and the trainer's reset protocol
 // (main.py:212-230) when autoreset is on.
 #pragma once
 #include "qr_env.cuh"
-
-#ifndef QR_OPT_PREFETCH
-#define QR_OPT_PREFETCH 0
-#endif
-#ifndef QR_OPT_LOCKSTEP
-#define QR_OPT_LOCKSTEP 0
-#endif
+#include "generated/actor_td3.cuh"
 
 namespace qr {
 
@@ -425,35 +420,11 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         ep_ret[1] = (G == 2) ? a.ep_return[N + e] : (T)0;
                         ep_len = a.ep_length[e];
                         ep_idx = a.ep_index[e];
-#if QR_OPT_PREFETCH
-                        // L2 prefetch of what this env.step reads later (goal rows, actions) ...
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) prefetch_l2(a.goal + i * N + e);
-                        if (a.actions) prefetch_l2((const char*)a.actions + (size_t)e * A * (a.act_f32 ? 4 : 8));
-                        // ... and of the env this lane will most likely take next (same lane of the next tile)
-                        const int64_t vn = v + 32;
-                        const int64_t en = a.env_lo + ((gw + (vn >> 5) * W) << 5) + (vn & 31);
-                        if (vn < vlen && en < a.env_hi) {
-#pragma unroll
-                            for (int i = 0; i < 18; ++i) prefetch_l2(a.state + i * N + en);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) prefetch_l2(a.integ + i * N + en);
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) prefetch_l2(a.params + i * N + en);
-                            prefetch_l2(a.ep_return + en); prefetch_l2(a.ep_length + en); prefetch_l2(a.ep_index + en);
-                        }
-#endif
                     }
                 }
             }
         }
-#if QR_OPT_LOCKSTEP
-        // all warps of the CTA move through phase A and phase B together: the instruction working set at any
-        // time is one phase, fetched once for twelve warps
-        if (!__syncthreads_or(busy ? 1 : 0)) break;
-#else
         if (!__any_sync(FULL, busy)) break;
-#endif
         // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
         if (busy && need_init) {
             need_init = false;
@@ -622,6 +593,37 @@ __global__ void __launch_bounds__(QR_BLOCK) k_norm_error_state(const StepArgs<T>
         for (int i = 0; i < 8; ++i) a.integ[i * a.n + e] = r.I[i];
     }
     for (int i = 0; i < O; ++i) a.obs[e * O + i] = o[i];
+}
+
+// ---- the reference's shipped TD3 actors, obs -> action on device (agent.choose_action(obs, explor_noise_std=0),
+// algos/td3/td3.py:93-96 with the checkpoints of main.py:101-110) -------------------------------------------------
+// One env per thread; the row-major observation tile of the block goes through shared memory so that the
+// global loads are full lines.  MODE 1: monolithic actor 23 -> 4.  MODE 2: module 1 (15 -> 4) and module 2 (3 -> 1).
+template <int MODE>
+__global__ void __launch_bounds__(QR_BLOCK) k_actor_td3(const float* __restrict__ obs, float* __restrict__ act, int64_t n)
+{
+    constexpr int O = (MODE == 1) ? 23 : 18;
+    constexpr int A = (MODE == 2) ? 5 : 4;
+    __shared__ float tile[QR_BLOCK * O];
+    const int tid = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * QR_BLOCK;
+    const int64_t rem = n - e0;
+    const int nvalid = (int)(rem < QR_BLOCK ? rem : QR_BLOCK);
+    for (int i = tid; i < nvalid * O; i += QR_BLOCK) tile[i] = obs[e0 * O + i];
+    __syncthreads();
+    if (tid >= nvalid) return;
+    float x[O], a[A];
+#pragma unroll
+    for (int i = 0; i < O; ++i) x[i] = tile[tid * O + i];
+    if (MODE == 1) {
+        actor_td3_mono(x, a);
+        *reinterpret_cast<float4*>(act + (e0 + tid) * 4) = make_float4(a[0], a[1], a[2], a[3]);
+    } else {
+        actor_td3_modul1(x, a);
+        actor_td3_modul2(x + 15, a + 4);
+#pragma unroll
+        for (int i = 0; i < A; ++i) act[(e0 + tid) * A + i] = a[i];
+    }
 }
 
 // ---- host-layout <-> device-layout (row-major [n][C] doubles <-> [C][n] T) -----------------------------------

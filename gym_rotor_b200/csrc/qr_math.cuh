@@ -9,9 +9,6 @@
 #include <math.h>
 
 #define QR_DEV __device__ __forceinline__
-#ifndef QR_OPT_NEWTON
-#define QR_OPT_NEWTON 1
-#endif
 
 namespace qr {
 
@@ -201,9 +198,7 @@ template <typename T, bool NEWTON = false> QR_DEV int ensure_so3(T* R)
 {
     T defect;
     if (so3_ok(R, &defect)) return 0;
-#if QR_OPT_NEWTON
     if (NEWTON) { if (defect < (T)0.05 && polar_newton<T>(R)) return 1; }
-#endif
     T tmp[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) tmp[i] = R[i];

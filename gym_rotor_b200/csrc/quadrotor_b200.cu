@@ -295,6 +295,20 @@ int qr_norm_error_state(qr_handle* h, const uint8_t* mask, void* stream)
     return QR_OK;
 }
 
+int qr_policy_td3(qr_handle* h, float* actions, void* stream)
+{
+    int rc = check(h); if (rc) return rc;
+    if (!actions) return fail(QR_ERR_INVALID, "qr_policy_td3: null actions");
+    if (h->cfg.mode == QR_MODE_QUAD) return fail(QR_ERR_INVALID, "qr_policy_td3: the reference ships no actor for the base Quad-v0 env");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned nb = blocks_for(h->cfg.n_envs);
+    if (h->cfg.mode == QR_MODE_COUPLED) qr::k_actor_td3<1><<<nb, qr::QR_BLOCK, 0, s>>>(h->obs, actions, h->cfg.n_envs);
+    else qr::k_actor_td3<2><<<nb, qr::QR_BLOCK, 0, s>>>(h->obs, actions, h->cfg.n_envs);
+    g_launches++;
+    QR_CUDA(cudaGetLastError());
+    return QR_OK;
+}
+
 int qr_step(qr_handle* h, const void* actions, int act_dtype, void* stream)
 {
     int rc = check(h); if (rc) return rc;

@@ -162,6 +162,14 @@ class BatchedQuadEnv:
                                   nat.F64 if action.dtype == torch.float64 else nat.F32, self._stream()))
         return self._split_obs(self.obs), self.reward, self.done.bool(), False, {}
 
+    def policy_td3(self, out=None):
+        """Actions of the reference's shipped TD3 actor(s) for the current observations, computed on device
+        (compiled effective weights; agent.choose_action(obs, explor_noise_std=0), td3.py:93-96)."""
+        if out is None:
+            out = torch.empty((self.num_envs, self.act_dim), dtype=torch.float32, device=self.device)
+        nat.check(self._L.qr_policy_td3(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def rollout(self, n_steps, actions=None, store=False):
         """n_steps fused env.step() calls in ONE kernel launch (state stays in registers).
 

@@ -119,6 +119,12 @@ int qr_norm_error_state(qr_handle* h, const uint8_t* mask, void* stream);
  * Outputs land in the qr_buffers views. */
 int qr_step(qr_handle* h, const void* actions, int act_dtype, void* stream);
 
+/* agent.choose_action(obs, explor_noise_std=0) (algos/td3/td3.py:93-96) for the TD3 actors the reference ships
+ * (models/TD3_*.pth, loaded at main.py:101-110): reads the handle's current observations, writes float32
+ * actions [N][A] (device).  The actors are compiled from their effective weights (tools/gen_actor_kernels.py);
+ * COUPLED uses the monolithic actor, DECOUPLED module 1 (f, tau) and module 2 (M3). */
+int qr_policy_td3(qr_handle* h, float* actions, void* stream);
+
 /* `n_steps` consecutive env.step() calls fused in one launch, state resident in registers.
  * actions: device [n_steps][N][A] or NULL = U(-1,1) actions drawn in-kernel with Philox (the synthetic
  * random-action workload).  obs_out/reward_out/done_out: device [n_steps][N][..] or NULL to keep only the

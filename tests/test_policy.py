@@ -57,3 +57,43 @@ def test_policy_in_the_loop_reproduces_reference_eval_episode(fw, tag, A):
     assert np.abs(ret - ep["reward"].sum(axis=0)).max() < 0.05, (ret, ep["reward"].sum(axis=0))
     assert ret[0] > 985
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fw,tag", [("MONO", "mono"), ("MODUL", "modul")])
+def test_compiled_actor_kernel_matches_reference_outputs(fw, tag):
+    """qr_policy_td3 (effective weights compiled to straight-line sm_100a code) vs the reference actors' outputs."""
+    from gym_rotor_b200 import vec_env
+    z = np.load(os.path.join(G, "policy_td3_%s.npz" % tag))
+    n = z["a0_obs"].shape[0]
+    env = vec_env.BatchedQuadEnv(n, framework=fw, dtype=torch.float32)
+    if fw == "MONO":
+        obs = z["a0_obs"]; ref = z["a0_act"]
+    else:
+        obs = np.concatenate([z["a0_obs"], z["a1_obs"]], axis=1); ref = np.concatenate([z["a0_act"], z["a1_act"]], axis=1)
+    env.obs.copy_(torch.as_tensor(obs, device="cuda:0"))
+    act = env.policy_td3().cpu().numpy()
+    assert act.shape == ref.shape and np.abs(act - ref).max() < 1e-4, np.abs(act - ref).max()
+    env.close()
+
+
+@pytest.mark.gpu
+def test_compiled_actor_in_the_loop_flies_the_reference_episode():
+    """Config 5 in miniature: env.step + compiled actor, both on device, 1000 steps against the reference's run."""
+    from gym_rotor_b200 import vec_env
+    ep = np.load(os.path.join(G, "eval_mono.npz"))
+    n = 32
+    env = vec_env.BatchedQuadEnv(n, framework="MONO", dtype=torch.float64, goal_mode="traj0")
+    env.set_state(np.tile(ep["state0"], (n, 1)), np.tile(ep["integ0"], (n, 1)), np.tile(ep["params"], (n, 1)),
+                  np.tile(ep["goal0"], (n, 1)))
+    env.obs.copy_(torch.as_tensor(np.tile(ep["obs0"], (n, 1)), device="cuda:0"))
+    ret = 0.0
+    for t in range(len(ep["reward"])):
+        act = env.policy_td3()
+        _, rew, done, _, _ = env.step(act.to(torch.float64))
+        ret += float(rew[0, 0])
+        assert not bool(done.any())
+    st = env.get_state()[0]
+    assert np.abs(st[0] - ep["state"][-1]).max() < 1e-3
+    assert abs(ret - ep["reward"].sum()) < 0.05 and ret > 985
+    env.close()
