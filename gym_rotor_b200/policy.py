@@ -3,7 +3,7 @@
 The shipped checkpoints (models/TD3_*.pth) are equivariant-MLP actors (algos/td3/td3_emlp.py:14-62,139-245;
 algos/emlp_torch/nn.py:13-99) that only work inside a module built under torch.manual_seed(1992).  Their
 EFFECTIVE per-layer maps were extracted once from a reference-constructed module by black-box probing
-(oracle/make_policy_fixture.py -> tests/golden/policy_td3_*.npz):
+(the fixture script make_policy_fixture.py -> tests/golden/policy_td3_*.npz):
 
     block:  lin = A x + b ;  pre = lin + q(lin),  q_i = sum_jk T_ijk lin_j lin_k ;  h = sigmoid(pre[gate]) * pre[:C]
     head:   action = tanh(A_out h + b_out)
