@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         // ---- A1: finish the env.step that just completed ----
         const unsigned finmask = __ballot_sync(FULL, fin);
         if (finmask) {
+            __syncwarp();   // phase B is over for every lane: the stage storage may be reused as reset scratch
             bool did_reset = false, term = false, trunc = false;
             int nf = 0, st = 0, nproj = 0, ep_len_done = 0;
             float rew0f = 0.f;
@@ -519,6 +520,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             ode.nproj += fl & 1;
         }
         // =============================== phase B ===============================
+        __syncwarp();       // scratch reads of phase A are done before any lane writes stage derivatives again
         {
             const bool live = busy && !fin;
             const bool f2 = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, lane, live);
