@@ -173,7 +173,48 @@ def make_batch():
           nfev=nfev, obs_crc=obs_crc, obs_last=obs_all[-1], actions_crc=np.uint32(zlib.crc32(actions.tobytes())))
 
 
+def make_traj():
+    """Trajectory generator modes 1 (hover), 5 (circle), 6 (figure eight) and the manual-mode fallback after a
+    trajectory completes (utils/trajectory_generator.py:113-173, 232-505), driven like main.py:304-331 with the shipped
+    MONO actor keeping the vehicle in the air.  One row per get_desired() call: input state, outputs, clock."""
+    import make_policy_fixture as mpf
+    args, agents = mpf.build_agents("MONO")
+    out = {}
+    for name, mode, steps, tweak in (("hover", 1, 600, None), ("circle", 5, 600, None), ("eight", 6, 700, None),
+                                     ("circle_manual", 5, 500, "short")):
+        env = rh.make_env("MONO")
+        tg = rh.make_trajgen(env)
+        if tweak == "short":
+            tg.num_circles = 0          # t_traj = 1.75 s: the circle ends after its straight segment -> manual mode
+        rh.seed_all(21 + mode)
+        state32 = env.reset(env_type="eval")
+        tg.mark_traj_start(state32)
+        rec = {k: [] for k in ("state", "goal", "b1d_dot", "t", "manual")}
+        xd, vd, b1d, b1d_dot, Wd = tg.get_desired(state32, mode)
+        rec["state"].append(np.array(state32, np.float64)); rec["goal"].append(np.concatenate([xd, vd, b1d, Wd]))
+        rec["b1d_dot"].append(np.array(b1d_dot, np.float64)); rec["t"].append(tg.t); rec["manual"].append(tg.manual_mode)
+        env.set_goal_state(xd, vd, b1d, b1d_dot, Wd)
+        obs_n = env.get_norm_error_state("MONO")
+        for _ in range(steps):
+            st = env.get_current_state()
+            xd, vd, b1d, b1d_dot, Wd = tg.get_desired(st, mode)
+            rec["state"].append(np.array(st, np.float64)); rec["goal"].append(np.concatenate([xd, vd, b1d, Wd]))
+            rec["b1d_dot"].append(np.array(b1d_dot, np.float64)); rec["t"].append(tg.t); rec["manual"].append(tg.manual_mode)
+            env.set_goal_state(xd, vd, b1d, b1d_dot, Wd)
+            act = agents[0].choose_action(obs_n[0], explor_noise_std=0.)
+            obs_n, rew, done, _, _ = env.step(act.copy())
+            if done[0]:
+                break
+        for k, v in rec.items():
+            out["%s_%s" % (name, k)] = np.array(v)
+        out["%s_draws" % name] = np.array([float(getattr(tg, "t_traj", 0.0)), float(getattr(tg, "w_b1d", 0.0)),
+                                           float(getattr(tg, "smooth_term", 0.0)), float(tg.theta_init)])
+        print(name, "calls", len(rec["t"]), "manual at end", rec["manual"][-1], "draws", out["%s_draws" % name])
+    _save("traj_modes.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["step", "kat1", "reset", "quad", "batch"]
+    which = sys.argv[1:] or ["step", "kat1", "reset", "quad", "batch", "traj"]
     for w in which:
-        {"step": make_step, "kat1": make_kat1, "reset": make_reset, "quad": make_quad, "batch": make_batch}[w]()
+        {"step": make_step, "kat1": make_kat1, "reset": make_reset, "quad": make_quad, "batch": make_batch,
+         "traj": make_traj}[w]()

@@ -332,6 +332,155 @@ int qo_traj_init_mode0_f64(int64_t n, const double* state, const double* theta, 
     return 0;
 }
 
+/* ---- trajectory generator, modes 1 / 5 / 6 and the manual fallback (utils/trajectory_generator.py:113-173, 232-505) ----
+ * Per-env trajectory state ts[n][12]:
+ *   0 t | 1 flags (bit0 trajectory_started, bit1 manual_mode, bit2 manual_mode_init) | 2..4 x_init / circle or eight centre |
+ *   5 theta_init | 6 w_b1d | 7 smooth_term (hover) | 8 t_traj | 9,10 b1d_dot x,y | 11 unused                                  */
+
+/* mark_traj_start (trajectory_generator.py:176-192): clock and flags to zero, initial heading from the state handed in
+ * (the float32 reset state in main.py:226-227). */
+int qo_traj_start_f64(int64_t n, const double* state, double* ts)
+{
+    for (int64_t e = 0; e < n; ++e) {
+        double R[9];
+        for (int i = 0; i < 9; ++i) R[i] = state[18 * e + 6 + i];
+        ensure_so3_f64(R, 0);
+        double* s = ts + 12 * e;
+        for (int i = 0; i < 12; ++i) s[i] = 0.0;
+        for (int i = 0; i < 3; ++i) s[2 + i] = state[18 * e + i];
+        s[5] = atan2(R[1], R[0]);
+    }
+    return 0;
+}
+
+/* One get_desired(state, mode) call (trajectory_generator.py:113-173) for mode 1 (hover), 5 (circle), >= 6 (figure
+ * eight).  goal[n][12] = xd vd b1d Wd is read and updated in place (several branches leave components untouched).
+ * numpy detail that is part of the observable behaviour: set_desired_states_to_current makes xd / vd COPIES of the
+ * state's x / v (:212-215); under main.py's protocol the trajectory starts from the float32 reset state
+ * (main.py:226-228), so xd and vd are float32 arrays for the whole trajectory and every element assignment rounds
+ * to float32 (F32 below).  After a switch to manual mode they are float64 copies of the then-current state.
+ * draws[n][2]: uniforms in [0,1) for the hover's t_traj ~ U(2,5) and w_b1d ~ U(-0.15 pi, 0.15 pi).  */
+#define F32(v) ((double)(float)(v))
+int qo_traj_desired_f64(int mode, int64_t n, const double* state, double* ts, double* goal, const double* draws, double dt)
+{
+    const double circle_radius = 0.7, circle_linear_v = 0.4, circle_W = 0.4;   /* :87-90 */
+    const int num_circles = 2;
+    const double eight_A1 = 1.5, eight_A2 = 1.0, eight_T = 9.0, eight_w_b1d = 0.349066;   /* :93-98 */
+    const int num_of_eights = 3;
+    const double eight_w1 = 2 * M_PI / eight_T, eight_w2 = 4 * M_PI / eight_T;
+    const double eight_exp_xy = -log(0.01) / eight_T, eight_alt_d = -0.6;       /* :101-105 */
+    for (int64_t e = 0; e < n; ++e) {
+        const double* y = state + 18 * e;
+        double R[9];
+        for (int i = 0; i < 9; ++i) R[i] = y[6 + i];
+        ensure_so3_f64(R, 0);
+        const double* x = y; const double* v = y + 3; const double* W = y + 15;
+        double* s = ts + 12 * e;
+        double* g = goal + 12 * e;
+        double* xd = g; double* vd = g + 3; double* b1d = g + 6; double* Wd = g + 9;
+        int flags = (int)s[1];
+        const double th_cur = atan2(R[1], R[0]);   /* get_current_b1 */
+        if (flags & 2) {   /* manual() :232-249; calculate_desired returns before the Wd block */
+            if (!(flags & 4)) {
+                for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; }
+                s[5] = th_cur;
+                flags |= 4;
+            }
+            vd[0] = vd[1] = vd[2] = 0.0;
+            b1d[0] = cos(s[5]); b1d[1] = sin(s[5]); b1d[2] = 0.0;
+            s[1] = (double)flags;
+            continue;
+        }
+        if (mode == 1) {   /* hovering :252-277 */
+            if (!(flags & 1)) {
+                for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; s[2 + i] = x[i]; }
+                b1d[0] = cos(th_cur); b1d[1] = sin(th_cur); b1d[2] = 0.0;
+                flags |= 1;
+                s[8] = 2.0 + (5.0 - 2.0) * draws[2 * e];
+                s[7] = -log(0.001) / s[8];
+                s[6] = -0.15 * M_PI + (0.15 * M_PI - (-0.15 * M_PI)) * draws[2 * e + 1];
+            }
+            s[0] = s[0] + dt;
+            const double t = s[0], k = s[7], w = s[6];
+            for (int i = 0; i < 3; ++i) {
+                xd[i] = F32((s[2 + i] - 0.0) * exp(-k * t) + 0.0);
+                vd[i] = F32(-(s[2 + i] - 0.0) * k * exp(-k * t));
+            }
+            b1d[0] = cos(w * t + s[5]); b1d[1] = sin(w * t + s[5]); b1d[2] = 0.0;
+            s[9] = -w * sin(w * t + s[5]); s[10] = w * cos(w * t + s[5]);
+        } else if (mode == 5) {   /* circle :359-412 */
+            if (!(flags & 1)) {
+                for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; s[2 + i] = x[i]; }
+                b1d[0] = cos(th_cur); b1d[1] = sin(th_cur); b1d[2] = 0.0;
+                flags |= 1;
+                s[8] = circle_radius / circle_linear_v + num_circles * 2 * M_PI / circle_W;
+            }
+            s[0] = s[0] + dt;
+            const double t = s[0];
+            if (t < circle_radius / circle_linear_v) {
+                /* np.float32 + python float -> float32 arithmetic (NEP 50): both operands rounded first */
+                xd[0] = (double)((float)s[2] + (float)(circle_linear_v * t));
+                vd[0] = F32(circle_linear_v);
+            } else if (t < s[8]) {
+                const double tt = t - circle_radius / circle_linear_v, th = circle_W * tt;
+                xd[0] = F32(circle_radius * cos(th) + s[2]);
+                vd[0] = F32(-circle_radius * circle_W * sin(th));
+                xd[1] = F32(circle_radius * sin(th) + s[3]);
+                vd[1] = F32(circle_radius * circle_W * cos(th));
+                const double thb = circle_W * tt + M_PI;
+                b1d[0] = cos(thb); b1d[1] = sin(thb); b1d[2] = 0.0;
+                s[9] = -circle_W * sin(thb); s[10] = circle_W * cos(thb);
+            } else {
+                flags |= 2;   /* mark_traj_end(True): manual mode from the next call on */
+            }
+        } else {   /* eight_shaped_curve :415-505 */
+            if (!(flags & 1)) {
+                for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; s[2 + i] = x[i]; }
+                b1d[0] = cos(th_cur); b1d[1] = sin(th_cur); b1d[2] = 0.0;
+                flags |= 1;
+                s[8] = num_of_eights * eight_T;
+                s[6] = eight_w_b1d;
+            }
+            s[0] = s[0] + dt;
+            const double t = s[0];
+            if (t < s[8]) {
+                const double ex = 1. - exp(-eight_exp_xy * t), dex = eight_exp_xy * exp(-eight_exp_xy * t);
+                xd[0] = F32(eight_A2 * (sin(eight_w2 * t) * ex) + s[2]);
+                vd[0] = F32(eight_A2 * ((eight_w2 * cos(eight_w2 * t) * ex) + (sin(eight_w2 * t) * dex)));
+                xd[1] = F32(eight_A1 * (cos(eight_w1 * t) - 1.) * ex + s[3]);
+                vd[1] = F32(eight_A1 * ((eight_w1 * -sin(eight_w1 * t) * ex) + (cos(eight_w1 * t) - 1.) * dex));
+                /* the altitude terms start from the float32 centre and only meet python floats: all float32 */
+                const float za = ((float)s[4] - (float)eight_alt_d) / 2.0f;
+                xd[2] = (double)(za * (float)(1 - cos(eight_w1 * t)) + (float)s[4]);
+                vd[2] = (double)((za * (float)eight_w1) * (float)sin(eight_w1 * t));
+                const double wt = s[6] * t * ex + s[5], dwt = s[6] * (ex + t * dex);
+                b1d[0] = cos(wt); b1d[1] = sin(wt); b1d[2] = 0.0;
+                s[9] = -sin(wt) * dwt; s[10] = cos(wt) * dwt;
+            } else {
+                flags |= 2;
+            }
+        }
+        s[1] = (double)flags;
+        /* Wd (:165-172) with the current b1d_dot */
+        const double* b3 = R + 6;
+        double b3d[3], bdd[3] = {s[9], s[10], 0.0};
+        for (int i = 0; i < 3; ++i) b3d[i] = R[i] * W[1] - R[i + 3] * W[0];
+        double dp = fma(b1d[2], b3[2], fma(b1d[1], b3[1], b1d[0] * b3[0]));
+        double dq = fma(b1d[2], b3d[2], fma(b1d[1], b3d[1], b1d[0] * b3d[0]));
+        double dr = fma(bdd[2], b3[2], fma(bdd[1], b3[1], bdd[0] * b3[0]));
+        double b1c[3], b1cd[3];
+        for (int i = 0; i < 3; ++i) {
+            b1c[i] = b1d[i] - dp * b3[i];
+            b1cd[i] = bdd[i] - ((dr * b3[i] + dq * b3[i]) + dp * b3d[i]);
+        }
+        double oc0 = b1c[1] * b1cd[2] - b1c[2] * b1cd[1];
+        double oc1 = b1c[2] * b1cd[0] - b1c[0] * b1cd[2];
+        double oc2 = b1c[0] * b1cd[1] - b1c[1] * b1cd[0];
+        Wd[0] = 0; Wd[1] = 0; Wd[2] = fma(b3[2], oc2, fma(b3[1], oc1, b3[0] * oc0));
+    }
+    return 0;
+}
+
 /* ---- Philox4x32-10 ----------------------------------------------------------------------------------- */
 
 void qo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])

@@ -61,6 +61,8 @@ def lib():
         L.qo_reset_from_uniforms_f64.argtypes = [C.POINTER(QoConfig), C.c_int, C.c_double, C.c_int64, dp, dp, dp, dp]
         L.qo_traj_wd_f64.argtypes = [C.c_int64, dp, dp, dp]
         L.qo_traj_init_mode0_f64.argtypes = [C.c_int64, dp, dp, dp]
+        L.qo_traj_start_f64.argtypes = [C.c_int64, dp, dp]
+        L.qo_traj_desired_f64.argtypes = [C.c_int, C.c_int64, dp, dp, dp, dp, C.c_double]
         L.qo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.qo_set_threads.argtypes = [C.c_int]
         L.qo_get_max_threads.restype = C.c_int
@@ -172,6 +174,22 @@ def traj_init_mode0(state, theta):
     out = np.empty((state.shape[0], 3))
     lib().qo_traj_init_mode0_f64(state.shape[0], _p(state, C.c_double), _p(theta, C.c_double), _p(out, C.c_double))
     return out
+
+
+def traj_start(state):
+    """mark_traj_start: fresh per-env trajectory state ts[n,12] from the (float32-valued) reset state."""
+    state = np.ascontiguousarray(state, np.float64)
+    ts = np.zeros((state.shape[0], 12))
+    lib().qo_traj_start_f64(state.shape[0], _p(state, C.c_double), _p(ts, C.c_double))
+    return ts
+
+
+def traj_desired(mode, state, ts, goal, draws, dt=1. / 200):
+    """One get_desired(state, mode) call for mode 1 / 5 / 6; ts and goal are updated in place."""
+    state = np.ascontiguousarray(state, np.float64); draws = np.ascontiguousarray(draws, np.float64)
+    assert ts.dtype == np.float64 and goal.dtype == np.float64 and ts.flags.c_contiguous and goal.flags.c_contiguous
+    lib().qo_traj_desired_f64(int(mode), state.shape[0], _p(state, C.c_double), _p(ts, C.c_double), _p(goal, C.c_double),
+                              _p(draws, C.c_double), float(dt))
 
 
 def philox4x32_10(ctr, key):

@@ -174,3 +174,26 @@ def test_trajgen_mode0_matches_reference():
     assert np.abs(ang).max() <= np.deg2rad(25) + 1e-12
     b1d_again = qo.traj_init_mode0(st32, ang)
     assert np.abs(b1d_again - g["goal"][~ok, 6:9]).max() < 1e-12
+
+
+@pytest.mark.parametrize("name,mode", [("hover", 1), ("circle", 5), ("eight", 6), ("circle_manual", 5)])
+def test_trajgen_modes_match_reference(name, mode):
+    """Modes 1 / 5 / 6 and the manual fallback, call by call against the reference's TrajectoryGenerator
+    (the hover's two random draws are injected from the reference run)."""
+    g = _load("traj_modes.npz")
+    st, goal_ref, bdd_ref, t_ref = g[name + "_state"], g[name + "_goal"], g[name + "_b1d_dot"], g[name + "_t"]
+    t_traj, w, smooth, theta0 = g[name + "_draws"]
+    draws = np.array([[(t_traj - 2.0) / 3.0, (w + 0.15 * np.pi) / (0.3 * np.pi)]])
+    ts = qo.traj_start(st[0:1])
+    if name != "circle_manual":          # manual() overwrites theta_init with the heading at the switch
+        assert abs(ts[0, 5] - theta0) < 1e-15
+    goal = np.zeros((1, 12)); goal[0, 6] = 1.0
+    worst = 0.0
+    for i in range(len(t_ref)):
+        qo.traj_desired(mode, st[i:i + 1], ts, goal, draws)
+        if name == "circle_manual" and int(ts[0, 1]) & 1 and ts[0, 8] > 2.0:
+            ts[0, 8] = 1.75            # the golden run shortened the circle (num_circles = 0) to reach manual mode
+        worst = max(worst, np.abs(goal[0] - goal_ref[i]).max(), np.abs(ts[0, 9:11] - bdd_ref[i, 0:2]).max())
+        assert abs(ts[0, 0] - t_ref[i]) < 1e-12
+    assert worst < 1e-11, worst
+    assert bool(int(ts[0, 1]) & 2) == bool(g[name + "_manual"][-1])
