@@ -14,7 +14,7 @@ MODE_QUAD, MODE_COUPLED, MODE_DECOUPLED = 0, 1, 2
 F32, F64 = 0, 1
 INT_DOP853, INT_EULER = 0, 1
 ENV_TRAIN, ENV_EVAL = 0, 1
-GOAL_EXTERNAL, GOAL_TRAJ_MODE0 = 0, 1
+GOAL_EXTERNAL, GOAL_TRAJ_MODE0, GOAL_TRAJ_HOVER, GOAL_TRAJ_CIRCLE, GOAL_TRAJ_EIGHT = 0, 1, 2, 3, 4
 ST_NONFINITE, ST_TOO_SMALL_STEP, ST_SVD = 1, 2, 4
 NUM_STATS = 16
 STAT_NAMES = ["episodes", "return0", "return1", "length", "crashed", "truncated", "return0_sq", "steps",
@@ -23,7 +23,7 @@ STAT_NAMES = ["episodes", "return0", "return1", "length", "crashed", "truncated"
 
 # every symbol include/quadrotor_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = ["qr_default_config", "qr_create", "qr_destroy", "qr_get_config", "qr_get_buffers", "qr_reset",
-           "qr_init_goal", "qr_norm_error_state", "qr_policy_td3", "qr_step", "qr_rollout", "qr_step_host", "qr_set_state_host",
+           "qr_init_goal", "qr_goal_update", "qr_norm_error_state", "qr_policy_td3", "qr_step", "qr_rollout", "qr_step_host", "qr_set_state_host",
            "qr_get_state_host", "qr_stats", "qr_launch_count", "qr_last_error", "qr_abi_version"]
 
 
@@ -43,7 +43,7 @@ class QrBuffers(C.Structure):
         "state", "integ", "params", "goal", "obs", "reward", "done", "terminated", "truncated", "final_obs", "nfev",
         "status", "ep_return", "ep_length", "ep_index", "stats")] + [
         ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("n_agents", C.c_int32), ("elem_size", C.c_int32),
-        ("n_envs", C.c_int64)]
+        ("n_envs", C.c_int64), ("traj", C.c_void_p)]
 
 
 class NativeError(RuntimeError):
@@ -71,6 +71,7 @@ def load():
     L.qr_get_buffers.argtypes = [vp, C.POINTER(QrBuffers)]
     L.qr_reset.argtypes = [vp, u8p, C.c_int, vp]
     L.qr_init_goal.argtypes = [vp, u8p, vp]
+    L.qr_goal_update.argtypes = [vp, vp]
     L.qr_norm_error_state.argtypes = [vp, u8p, vp]
     L.qr_policy_td3.argtypes = [vp, vp, vp]
     L.qr_step.argtypes = [vp, vp, C.c_int, vp]

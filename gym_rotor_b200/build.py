@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libquadrotor_b200.so")
 SOURCES = ["quadrotor_b200.cu"]
-DEPS = ["quadrotor_b200.cu", "qr_kernels.cuh", "qr_env.cuh", "qr_dop853.cuh", "qr_math.cuh", "dop853_tableau.h",
+DEPS = ["quadrotor_b200.cu", "qr_kernels.cuh", "qr_env.cuh", "qr_traj.cuh", "qr_dop853.cuh", "qr_math.cuh", "dop853_tableau.h",
         os.path.join("generated", "actor_td3.cuh"),
         os.path.join("..", "..", "include", "quadrotor_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -11,6 +11,7 @@
 // (main.py:212-230) when autoreset is on.
 #pragma once
 #include "qr_env.cuh"
+#include "qr_traj.cuh"
 #include "generated/actor_td3.cuh"
 
 namespace qr {
@@ -29,6 +30,7 @@ template <typename T> struct StepArgs {
     int64_t env_id_offset;     // global id of local env 0
     uint32_t key0, key1;       // Philox key = seed
     T *state, *integ, *params, *goal;
+    T* traj;                   // [12][n] trajectory-generator state (goal modes hover / circle / eight)
     float* obs; T* reward; uint8_t *done, *terminated, *truncated; float* final_obs;
     int32_t* nfev; uint8_t* status; T* ep_return; int32_t* ep_length; uint32_t* ep_index; double* stats;
     const void* actions;       // [n_steps][n][A] f32|f64, or nullptr -> Philox U(-1,1)
@@ -103,7 +105,14 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
     T theta;
     reset_env<T>(r, ph, gid, episode, c.env_type, c.udm, &theta);
     if (c.goal_mode == 1) init_goal_mode0<T>(r, theta);
-    else {
+    else if (c.goal_mode >= 2) {
+        T ts[12];
+        uint32_t rnd[4];
+        ph((uint32_t)gid, (uint32_t)(gid >> 32), episode, QR_DOMAIN_RESET + 5u, rnd);
+        traj_restart<T>(c.goal_mode, r, ts, r.goal, u01t<T>(rnd[0]), u01t<T>(rnd[1]), c.dt);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) a.traj[i * a.n + e] = ts[i];
+    } else {
 #pragma unroll
         for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * a.n + e];
     }
@@ -127,7 +136,7 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
 #pragma unroll
     for (int i = 0; i < 8; ++i) scratch[18 + i] = r.I[i];
     scratch[26] = r.m; scratch[27] = r.d; scratch[28] = r.J1; scratch[29] = r.J3; scratch[30] = r.c_tf; scratch[31] = r.c_tw;
-    store_params_goal(r, a, e, true, c.goal_mode == 1);
+    store_params_goal(r, a, e, true, c.goal_mode >= 1);
 #pragma unroll
     for (int i = 0; i < O; ++i) orow[i] = o[i];   // replaces the terminal observation in the caller's tile row
 }
@@ -568,9 +577,37 @@ __global__ void __launch_bounds__(QR_BLOCK) k_init_goal(const StepArgs<T> a, con
     load_env(r, a, e);
     uint32_t rnd[4];
     ph((uint32_t)gid, (uint32_t)(gid >> 32), a.ep_index[e], QR_DOMAIN_RESET + 4u, rnd);
-    T theta = ((T)-25 + (T)50 * u01t<T>(rnd[3])) * ((T)3.14159265358979323846 / (T)180);
-    init_goal_mode0<T>(r, theta);
+    if (a.c.goal_mode >= 2) {
+        T ts[12];
+        ph((uint32_t)gid, (uint32_t)(gid >> 32), a.ep_index[e], QR_DOMAIN_RESET + 5u, rnd);
+        traj_restart<T>(a.c.goal_mode, r, ts, r.goal, u01t<T>(rnd[0]), u01t<T>(rnd[1]), a.c.dt);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) a.traj[i * a.n + e] = ts[i];
+    } else {
+        T theta = ((T)-25 + (T)50 * u01t<T>(rnd[3])) * ((T)3.14159265358979323846 / (T)180);
+        init_goal_mode0<T>(r, theta);
+    }
     store_params_goal(r, a, e, false, true);
+}
+
+// ---- trajectory_generator.get_desired(state, mode) before every step, modes hover / circle / eight (main.py:145-147) --
+template <typename T>
+__global__ void __launch_bounds__(QR_BLOCK) k_goal_update(const StepArgs<T> a)
+{
+    const int64_t e = a.env_lo + (int64_t)blockIdx.x * QR_BLOCK + threadIdx.x;
+    if (e >= a.env_hi) return;
+    const int64_t N = a.n;
+    T x[3], v[3], R[9], W[3], ts[12], goal[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { x[i] = a.state[i * N + e]; v[i] = a.state[(3 + i) * N + e]; W[i] = a.state[(15 + i) * N + e]; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = a.state[(6 + i) * N + e];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { ts[i] = a.traj[i * N + e]; goal[i] = a.goal[i * N + e]; }
+    ensure_so3<T>(R);   // get_desired -> state_decomposition
+    traj_desired<T>(traj_ref_mode(a.c.goal_mode), x, v, R, W, ts, goal, (T)0, (T)0, a.c.dt);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { a.traj[i * N + e] = ts[i]; a.goal[i * N + e] = goal[i]; }
 }
 
 // ---- env.get_norm_error_state(framework) ---------------------------------------------------------------------

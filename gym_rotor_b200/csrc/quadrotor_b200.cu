@@ -40,7 +40,7 @@ struct qr_handle {
     int elem;  // sizeof(T)
     int O, A, G;
     // device buffers
-    void *state, *integ, *params, *goal, *reward, *ep_return;
+    void *state, *integ, *params, *goal, *reward, *ep_return, *traj;
     float *obs, *final_obs;
     uint8_t *done, *terminated, *truncated, *status;
     int32_t *nfev, *ep_length;
@@ -75,7 +75,7 @@ template <typename T> qr::StepArgs<T> make_args(const qr_handle* h)
     a.c.env_type = c.env_type; a.c.max_episode_steps = c.max_episode_steps; a.c.diagnostics = c.reserved0;
     a.n = c.n_envs; a.env_lo = 0; a.env_hi = c.n_envs; a.env_id_offset = c.env_id_offset;
     a.key0 = (uint32_t)c.seed; a.key1 = (uint32_t)(c.seed >> 32);
-    a.state = (T*)h->state; a.integ = (T*)h->integ; a.params = (T*)h->params; a.goal = (T*)h->goal;
+    a.state = (T*)h->state; a.integ = (T*)h->integ; a.params = (T*)h->params; a.goal = (T*)h->goal; a.traj = (T*)h->traj;
     a.obs = h->obs; a.reward = (T*)h->reward; a.done = h->done; a.terminated = h->terminated; a.truncated = h->truncated;
     a.final_obs = h->final_obs; a.nfev = h->nfev; a.status = h->status; a.ep_return = (T*)h->ep_return;
     a.ep_length = h->ep_length; a.ep_index = h->ep_index; a.stats = h->stats;
@@ -160,8 +160,9 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     if (c->dtype != QR_F32 && c->dtype != QR_F64) return fail(QR_ERR_INVALID, "qr_create: bad dtype");
     if (c->integrator == QR_INT_EULER && c->mode != QR_MODE_QUAD)
         return fail(QR_ERR_INVALID, "qr_create: the Euler integrator exists only for the base Quad-v0 env (quad.py:252)");
-    if (c->goal_mode == QR_GOAL_TRAJ_MODE0 && c->mode == QR_MODE_QUAD)
-        return fail(QR_ERR_INVALID, "qr_create: goal_mode TRAJ_MODE0 needs a wrapper mode");
+    if (c->goal_mode < QR_GOAL_EXTERNAL || c->goal_mode > QR_GOAL_TRAJ_EIGHT) return fail(QR_ERR_INVALID, "qr_create: bad goal_mode");
+    if (c->goal_mode != QR_GOAL_EXTERNAL && c->mode == QR_MODE_QUAD)
+        return fail(QR_ERR_INVALID, "qr_create: on-device goal generation needs a wrapper mode");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -178,7 +179,7 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     h->G = (c->mode == QR_MODE_DECOUPLED) ? 2 : 1;
     const size_t n = (size_t)c->n_envs, E = (size_t)h->elem;
     struct { void** p; size_t bytes; } allocs[] = {
-        {&h->state, 18 * n * E}, {&h->integ, 8 * n * E}, {&h->params, 6 * n * E}, {&h->goal, 12 * n * E},
+        {&h->state, 18 * n * E}, {&h->integ, 8 * n * E}, {&h->params, 6 * n * E}, {&h->goal, 12 * n * E}, {&h->traj, 12 * n * E},
         {(void**)&h->obs, n * h->O * 4}, {&h->reward, n * h->G * E}, {(void**)&h->done, n * h->G},
         {(void**)&h->terminated, n}, {(void**)&h->truncated, n}, {(void**)&h->final_obs, n * h->O * 4},
         {(void**)&h->nfev, n * 4}, {(void**)&h->status, n}, {&h->ep_return, 2 * n * E}, {(void**)&h->ep_length, n * 4},
@@ -231,7 +232,7 @@ int qr_destroy(qr_handle* h)
 {
     if (!h) return QR_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->state, h->integ, h->params, h->goal, h->obs, h->reward, h->done, h->terminated, h->truncated,
+    void* ptrs[] = {h->traj, h->state, h->integ, h->params, h->goal, h->obs, h->reward, h->done, h->terminated, h->truncated,
                     h->final_obs, h->nfev, h->status, h->ep_return, h->ep_length, h->ep_index, h->stats, h->d_actions, h->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->io_stream) cudaStreamDestroy(h->io_stream);
@@ -253,6 +254,7 @@ int qr_get_buffers(qr_handle* h, qr_buffers* b)
     b->obs = h->obs; b->reward = h->reward; b->done = h->done; b->terminated = h->terminated; b->truncated = h->truncated;
     b->final_obs = h->final_obs; b->nfev = h->nfev; b->status = h->status; b->ep_return = h->ep_return;
     b->ep_length = h->ep_length; b->ep_index = h->ep_index; b->stats = h->stats;
+    b->traj = h->traj;
     b->obs_dim = h->O; b->act_dim = h->A; b->n_agents = h->G; b->elem_size = h->elem; b->n_envs = h->cfg.n_envs;
     return QR_OK;
 }
@@ -278,6 +280,19 @@ int qr_init_goal(qr_handle* h, const uint8_t* mask, void* stream)
     const unsigned nb = blocks_for(h->cfg.n_envs);
     if (h->cfg.dtype == QR_F64) qr::k_init_goal<double><<<nb, qr::QR_BLOCK, 0, s>>>(make_args<double>(h), mask);
     else qr::k_init_goal<float><<<nb, qr::QR_BLOCK, 0, s>>>(make_args<float>(h), mask);
+    g_launches++;
+    QR_CUDA(cudaGetLastError());
+    return QR_OK;
+}
+
+int qr_goal_update(qr_handle* h, void* stream)
+{
+    int rc = check(h); if (rc) return rc;
+    if (h->cfg.goal_mode < QR_GOAL_TRAJ_HOVER) return QR_OK;   // external goals / mode 0 (evaluated inside qr_step)
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned nb = blocks_for(h->cfg.n_envs);
+    if (h->cfg.dtype == QR_F64) qr::k_goal_update<double><<<nb, qr::QR_BLOCK, 0, s>>>(make_args<double>(h));
+    else qr::k_goal_update<float><<<nb, qr::QR_BLOCK, 0, s>>>(make_args<float>(h));
     g_launches++;
     QR_CUDA(cudaGetLastError());
     return QR_OK;
@@ -324,6 +339,8 @@ int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, fl
 {
     int rc = check(h); if (rc) return rc;
     if (n_steps <= 0) return fail(QR_ERR_INVALID, "qr_rollout: n_steps must be positive");
+    if (n_steps > 1 && h->cfg.goal_mode >= QR_GOAL_TRAJ_HOVER)
+        return fail(QR_ERR_INVALID, "qr_rollout: trajectory modes hover/circle/eight need qr_goal_update before every step (n_steps must be 1)");
     if (actions && act_dtype != QR_F32 && act_dtype != QR_F64) return fail(QR_ERR_INVALID, "qr_rollout: bad act_dtype");
     cudaStream_t s = (cudaStream_t)stream;
     if (h->cfg.dtype == QR_F64) return launch_step<double>(h, 0, h->cfg.n_envs, actions, act_dtype, n_steps, obs_out, reward_out, done_out, s);

@@ -45,7 +45,8 @@ class BatchedQuadEnv:
         nat.check(self._L.qr_default_config(C.byref(cfg), _FRAMEWORKS[framework], nat.F64 if dtype == torch.float64 else nat.F32))
         cfg.n_envs = int(num_envs); cfg.env_id_offset = int(env_id_offset); cfg.seed = int(seed)
         cfg.autoreset = int(bool(autoreset))
-        cfg.goal_mode = {"external": nat.GOAL_EXTERNAL, "traj0": nat.GOAL_TRAJ_MODE0}[goal_mode]
+        cfg.goal_mode = {"external": nat.GOAL_EXTERNAL, "traj0": nat.GOAL_TRAJ_MODE0, "hover": nat.GOAL_TRAJ_HOVER,
+                         "circle": nat.GOAL_TRAJ_CIRCLE, "eight": nat.GOAL_TRAJ_EIGHT}[goal_mode]
         cfg.env_type = nat.ENV_TRAIN if env_type == "train" else nat.ENV_EVAL
         cfg.max_episode_steps = int(max_episode_steps)
         cfg.diagnostics = int(bool(diagnostics))
@@ -69,6 +70,7 @@ class BatchedQuadEnv:
         self.integ_soa = _view(b.integ, (8, N), ts, d)
         self.params_soa = _view(b.params, (6, N), ts, d)
         self.goal_soa = _view(b.goal, (12, N), ts, d)
+        self.traj_soa = _view(b.traj, (12, N), ts, d)
         self.obs = _view(b.obs, (N, O), "<f4", d)
         self.reward = _view(b.reward, (N, G), ts, d)
         self.done = _view(b.done, (N, G), "|u1", d)
@@ -127,6 +129,10 @@ class BatchedQuadEnv:
         keep, p = self._mask_ptr(mask)
         nat.check(self._L.qr_init_goal(self._h, p, self._stream()))
 
+    def goal_update(self):
+        """trajectory_generator.get_desired + set_goal_state for the hover / circle / eight goal modes (no-op otherwise)."""
+        nat.check(self._L.qr_goal_update(self._h, self._stream()))
+
     def get_current_state(self):
         """Live [N,18] view of the device state (the reference returns a live alias too, quad.py:409-410)."""
         return self.state_soa.t()
@@ -158,6 +164,8 @@ class BatchedQuadEnv:
             action = action.to(self.device).contiguous()
         if tuple(action.shape) != (self.num_envs, self.act_dim):
             raise ValueError("action must have shape (%d, %d)" % (self.num_envs, self.act_dim))
+        if self.cfg.goal_mode >= nat.GOAL_TRAJ_HOVER:
+            self.goal_update()      # trajectory_generator.get_desired on the pre-step state, main.py:145-147
         nat.check(self._L.qr_step(self._h, C.c_void_p(action.data_ptr()),
                                   nat.F64 if action.dtype == torch.float64 else nat.F32, self._stream()))
         return self._split_obs(self.obs), self.reward, self.done.bool(), False, {}
@@ -285,7 +293,7 @@ class QuadVectorEnv:
     def reset(self, *, seed=None, options=None):
         e = self.env
         e.reset(env_type="train" if e.cfg.env_type == nat.ENV_TRAIN else "eval")
-        if e.cfg.goal_mode == nat.GOAL_TRAJ_MODE0:
+        if e.cfg.goal_mode != nat.GOAL_EXTERNAL:
             e.init_goal()
         obs = e.get_norm_error_state()
         return obs[0] if len(obs) == 1 else obs, {}

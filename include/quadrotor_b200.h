@@ -40,7 +40,8 @@ enum { QR_MODE_QUAD = 0, QR_MODE_COUPLED = 1, QR_MODE_DECOUPLED = 2 };   /* Quad
 enum { QR_F32 = 0, QR_F64 = 1 };
 enum { QR_INT_DOP853 = 0, QR_INT_EULER = 1 };                            /* quad.py:62 */
 enum { QR_ENV_TRAIN = 0, QR_ENV_EVAL = 1 };                              /* reset(env_type=...) quad.py:171 */
-enum { QR_GOAL_EXTERNAL = 0, QR_GOAL_TRAJ_MODE0 = 1 };                   /* set_goal_state | on-device trajectory_generator mode 0 */
+/* set_goal_state | on-device trajectory_generator: mode 0 (idle, evaluated inside qr_step), 1 hover, 5 circle, 6 figure eight */
+enum { QR_GOAL_EXTERNAL = 0, QR_GOAL_TRAJ_MODE0 = 1, QR_GOAL_TRAJ_HOVER = 2, QR_GOAL_TRAJ_CIRCLE = 3, QR_GOAL_TRAJ_EIGHT = 4 };
 /* per-env status bits (the reference raises / ignores sol.status instead: coupled:63-64) */
 enum { QR_ST_NONFINITE = 1, QR_ST_TOO_SMALL_STEP = 2, QR_ST_SVD = 4 };
 /* indices into the 16-double statistics vector of qr_stats */
@@ -89,6 +90,7 @@ typedef struct qr_buffers {
     double* stats;              /* [QR_NUM_STATS] device accumulators */
     int32_t obs_dim, act_dim, n_agents, elem_size;
     int64_t n_envs;
+    void* traj;                 /* [12][N] T trajectory-generator state: t | flags | centre(3) | theta_init | w_b1d | smooth | t_traj | b1d_dot(2) | - */
 } qr_buffers;
 
 /* Fills *c with the reference's defaults for `mode`/`dtype` (args_parse.py, quad.py:28-107). */
@@ -107,8 +109,13 @@ int qr_reset(qr_handle* h, const uint8_t* mask, int env_type, void* stream);
 
 /* trajectory_generator.mark_traj_start + get_desired(mode 0) after a reset (main.py:127-128,227-229;
  * trajectory_generator.py:141-148,165-172): b1d = Rz(theta) [cos psi, sin psi, 0], xd = vd = 0.
- * Only for goal_mode = QR_GOAL_TRAJ_MODE0.  mask as in qr_reset. */
+ * For the other on-device goal modes: mark_traj_start + the first get_desired of that mode.  mask as in qr_reset. */
 int qr_init_goal(qr_handle* h, const uint8_t* mask, void* stream);
+
+/* trajectory_generator.get_desired(env.get_current_state(), mode) + env.set_goal_state, called by the trainer before
+ * every step (main.py:145-147), for goal_mode HOVER / CIRCLE / EIGHT (utils/trajectory_generator.py:252-277,359-505,
+ * manual fallback 232-249).  No-op for external goals and for mode 0. */
+int qr_goal_update(qr_handle* h, void* stream);
 
 /* env.get_norm_error_state(framework) (quad.py:421-466): writes obs from the CURRENT state and goal and,
  * like the reference, advances the integral terms once (main.py:129,230,314). */

@@ -388,3 +388,75 @@ def test_status_flags_nonfinite_state():
     assert status[5] & 1 and (np.delete(status, 5) == 0).all()
     assert np.isfinite(np.delete(env.get_state()[0], 5, axis=0)).all()
     env.close()
+
+
+@pytest.mark.parametrize("name,gm", [("hover", "hover"), ("circle", "circle"), ("eight", "eight"), ("circle_manual", "circle")])
+def test_trajectory_modes_match_reference(name, gm):
+    """qr_init_goal + qr_goal_update (modes 1 / 5 / 6 and the manual fallback) call by call against the reference's
+    TrajectoryGenerator driven along a real flight (tests/golden/traj_modes.npz)."""
+    g = _load("traj_modes.npz")
+    st, goal_ref, bdd_ref, t_ref = g[name + "_state"], g[name + "_goal"], g[name + "_b1d_dot"], g[name + "_t"]
+    t_traj, w, smooth, theta0 = g[name + "_draws"]
+    env = _env(1, "MONO", goal_mode=gm)
+    par = np.array([[2.15, 0.23, 0.022, 0.035, 0.0135, 2.2]])
+    env.set_state(st[0:1], np.zeros((1, 8)), par, None)
+    env.init_goal()                                 # mark_traj_start + first get_desired on the float32 reset state
+    ts = env.traj_soa
+    if name == "hover":                             # inject the reference run's two random draws
+        ts[8, 0] = t_traj; ts[7, 0] = smooth; ts[6, 0] = w
+    if name == "circle_manual":
+        ts[8, 0] = 1.75                             # the golden run shortened the circle to reach manual mode
+    start = 1 if name == "hover" else 0
+    if start == 0:
+        assert np.abs(env.get_state()[3][0] - goal_ref[0]).max() < 1e-11
+    worst = 0.0
+    for i in range(1, len(t_ref)):
+        env.set_state(st[i:i + 1], None, None, None)
+        env.goal_update()
+        gl = env.get_state()[3][0]
+        worst = max(worst, np.abs(gl - goal_ref[i]).max(), float((ts[9:11, 0].cpu() - torch.as_tensor(bdd_ref[i, 0:2])).abs().max()))
+        if i % 50 == 0:
+            assert abs(float(ts[0, 0]) - t_ref[i]) < 1e-12
+    assert worst < 1e-11, worst
+    assert bool(int(ts[1, 0]) & 2) == bool(g[name + "_manual"][-1])
+    env.close()
+
+
+def test_trajectory_modes_batch_vs_oracle_with_philox_draws():
+    """Hover mode on 512 envs: the per-env random draws come from the env's Philox stream (block 5 of the episode)."""
+    n, seed = 512, 13
+    env = _env(n, "MODUL", seed=seed, goal_mode="hover")
+    env.reset(); env.init_goal()
+    st = env.get_state()[0]
+    draws = np.empty((n, 2))
+    for i in range(n):
+        wds = qo.philox4x32_10([i, 0, 1, 5], [seed, 0])
+        draws[i] = [(wds[0] + 0.5) * 2.0 ** -32, (wds[1] + 0.5) * 2.0 ** -32]
+    st32 = st.astype(np.float32).astype(np.float64)
+    ts = qo.traj_start(st32)
+    goal = np.zeros((n, 12)); goal[:, 6] = 1.0
+    qo.traj_desired(1, st32, ts, goal, draws)
+    assert np.abs(env.get_state()[3] - goal).max() < 1e-12
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        obs, rew, done, _, _ = env.step(_t(rng.uniform(-0.2, 0.2, (n, 5)), torch.float64))   # step() runs goal_update first
+        # the oracle sees the same pre-step state the goal kernel saw
+        qo.traj_desired(1, st, ts, goal, draws)
+        assert np.abs(env.get_state()[3] - goal).max() < 1e-12
+        st = env.get_state()[0]
+    assert np.abs(env.traj_soa.t().cpu().numpy() - ts).max() < 1e-12
+    env.close()
+
+
+def test_trajectory_mode_autoreset_restarts_the_trajectory():
+    n = 1024
+    env = _env(n, "MONO", torch.float32, seed=4, goal_mode="eight", autoreset=True, max_episode_steps=40)
+    env.reset(); env.init_goal(); env.get_norm_error_state()
+    g = torch.Generator(device="cuda:0"); g.manual_seed(1)
+    for t in range(45):
+        env.step(torch.rand((n, 4), device="cuda:0", generator=g) * 0.2 - 0.1)
+    tclock = env.traj_soa[0].cpu().numpy()
+    # every env was reset at step 40 (time limit) at the latest: the clock restarted (dt per call, one call at restart)
+    assert tclock.max() <= 6 * 0.005 + 1e-6 and tclock.min() >= 0.005 - 1e-7
+    assert int(env.stats()[0]) >= n
+    env.close()
