@@ -115,8 +115,8 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
             xd[1] = f32r<T>(A1 * (c1 - (T)1) * ex + ts[3]);
             vd[1] = f32r<T>(A1 * ((w1 * -s1 * ex) + (c1 - (T)1) * dex));
             const float za = ((float)ts[4] - (float)(T)-0.6) / 2.0f;    // float32 centre meets python floats only
-            xd[2] = (T)(za * (float)((T)1 - c1) + (float)ts[4]);
-            vd[2] = (T)((za * (float)w1) * (float)s1);
+            xd[2] = (T)__fadd_rn(__fmul_rn(za, (float)((T)1 - c1)), (float)ts[4]);   // numpy: separate float32 multiply and add
+            vd[2] = (T)__fmul_rn(__fmul_rn(za, (float)w1), (float)s1);
             const T wt = ts[6] * t * ex + ts[5], dwt = ts[6] * (ex + t * dex);
             sincos_acc<T>(wt, &sn, &cs);
             b1d[0] = cs; b1d[1] = sn; b1d[2] = 0;

@@ -274,6 +274,30 @@ class QuadEnv(BatchedQuadEnv):
         super().__init__(num_envs, framework="QUAD", **kw)
 
 
+def benchmark_reward(obs_n, framework, x_lim=1.0):
+    """utils/utils.py:21-47 batched: interp(-||ex|| - |eb1|, [-2, 0], [0, 1]) with ex = obs[0:3] * x_lim and
+    eb1 = obs[18] * pi (MONO) or obs2[0] * pi (MODUL).  obs_n: list of observation tensors as step() returns them."""
+    o = obs_n[0]
+    ex = o[:, 0:3].double() * x_lim
+    eb1 = (obs_n[1][:, 0] if framework == "MODUL" else o[:, 18]).double() * np.pi
+    r = -torch.linalg.vector_norm(ex, dim=1) - eb1.abs()
+    return torch.clamp((r + 2.0) / 2.0, 0.0, 1.0)
+
+
+def time_limit_relabel(obs_n, reward, done, framework, x_lim=1.0):
+    """The trainer's relabel when an episode hits max_steps (main.py:169-173): done_n[0] becomes "solved" =
+    all(|ex| <= 0.03 m) and reward != -1; for MODUL done_n[1] = |eb1| <= 0.03 rad and reward != -1.
+    Returns the relabelled done tensor [N, G] (to be applied to the truncated envs only)."""
+    o = obs_n[0]
+    ex = o[:, 0:3].double() * x_lim
+    out = done.clone().bool()
+    out[:, 0] = (ex.abs() <= 0.03).all(dim=1) & (reward[:, 0] != -1.0)
+    if framework == "MODUL":
+        eb1 = obs_n[1][:, 0].double() * np.pi
+        out[:, 1] = (eb1.abs() <= 0.03) & (reward[:, 1] != -1.0)
+    return out
+
+
 class QuadVectorEnv:
     """gymnasium.vector.VectorEnv-shaped facade (gymnasium itself is not installed in this image).
 
@@ -301,7 +325,11 @@ class QuadVectorEnv:
     def step(self, actions):
         e = self.env
         obs, rew, done, _, _ = e.step(actions)
+        trunc = e.truncated.bool()
         info = {"final_obs": e.final_obs, "done_n": done}
+        if bool(trunc.any()):   # main.py:169-173: what the trainer stores as done_n for episodes that hit the limit
+            fin = e._split_obs(e.final_obs)
+            info["time_limit_done_n"] = time_limit_relabel(fin, rew, done, e.framework, e.x_lim)
         return (obs[0] if len(obs) == 1 else obs), rew, e.terminated.bool(), e.truncated.bool(), info
 
     def close(self):

@@ -456,7 +456,9 @@ def test_trajectory_mode_autoreset_restarts_the_trajectory():
     for t in range(45):
         env.step(torch.rand((n, 4), device="cuda:0", generator=g) * 0.2 - 0.1)
     tclock = env.traj_soa[0].cpu().numpy()
-    # every env was reset at step 40 (time limit) at the latest: the clock restarted (dt per call, one call at restart)
-    assert tclock.max() <= 6 * 0.005 + 1e-6 and tclock.min() >= 0.005 - 1e-7
+    # every env was reset at step 40 (time limit) at the latest; a restart makes one get_desired call (t = dt) and
+    # every later step one more, so the trajectory clock follows the episode length
+    eplen = env.ep_length.cpu().numpy()
+    assert eplen.max() <= 40 and np.abs(tclock - (1 + eplen) * 0.005).max() < 1e-6
     assert int(env.stats()[0]) >= n
     env.close()

@@ -97,3 +97,23 @@ def test_compiled_actor_in_the_loop_flies_the_reference_episode():
     assert np.abs(st[0] - ep["state"][-1]).max() < 1e-3
     assert abs(ret - ep["reward"].sum()) < 0.05 and ret > 985
     env.close()
+
+
+def test_trainer_side_helpers_match_reference_formulas():
+    """benchmark_reward (utils/utils.py:42-47 on get_error_state, :21-39) and the time-limit relabel (main.py:169-173)."""
+    from gym_rotor_b200.vec_env import benchmark_reward, time_limit_relabel
+    rng = np.random.default_rng(0)
+    obs = rng.uniform(-0.05, 0.05, (64, 23)).astype(np.float32)
+    obs[::4, 0:3] *= 0.1
+    o_t = [torch.as_tensor(obs)]
+    ex = obs[:, 0:3].astype(np.float64) * 1.0; eb1 = obs[:, 18].astype(np.float64) * np.pi
+    ref = np.interp(-np.linalg.norm(ex, axis=1) - np.abs(eb1), [-2., 0.], [0., 1.])
+    assert np.abs(benchmark_reward(o_t, "MONO").numpy() - ref).max() < 1e-12
+    rew = torch.as_tensor(rng.uniform(0, 1, (64, 1))); rew[5, 0] = -1.0
+    done = torch.zeros((64, 1), dtype=torch.bool)
+    rel = time_limit_relabel(o_t, rew, done, "MONO").numpy()[:, 0]
+    exp = (np.abs(ex) <= 0.03).all(axis=1) & (rew.numpy()[:, 0] != -1.0)
+    assert (rel == exp).all() and rel.any() and not rel.all()
+    o1 = torch.as_tensor(obs[:, :15]); o2 = torch.as_tensor(obs[:, 15:18])
+    refm = np.interp(-np.linalg.norm(ex, axis=1) - np.abs(obs[:, 15].astype(np.float64) * np.pi), [-2., 0.], [0., 1.])
+    assert np.abs(benchmark_reward([o1, o2], "MODUL").numpy() - refm).max() < 1e-12
