@@ -195,6 +195,7 @@ template <typename T> struct OdeLane {
     int nfev;       // as scipy counts: 2 + 12 * attempts
     int status;     // QR_ST_* bits
     int nproj;      // SO(3) re-projections inside RHS evaluations
+    int checked;    // the next attempt re-projects failing stage matrices (redo of a speculative attempt)
 };
 
 // RungeKutta.__init__: f0 = F(y0) -> K0, then select_initial_step.  (2 RHS evaluations)
@@ -202,7 +203,7 @@ template <typename T>
 QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T Tend, const T rtol, const T atol, T* K0, OdeLane<T>& o)
 {
     using N = num<T>;
-    o.t = 0; o.rejected = 0; o.nfev = 2; o.status = 0; o.nproj = 0;
+    o.t = 0; o.rejected = 0; o.nfev = 2; o.status = 0; o.nproj = 0; o.checked = 0;
     int fl = rhs14<T, false, false>(y, W3, d, K0);   // y's R was SO(3)-checked by the caller (observation_wrapper)
     o.nproj += fl & 1; if (fl & 2) o.status |= 4;
     T s0 = 0, s1 = 0;   // sums of (y/sc)^2 and (f0/sc)^2 over all 18 components
@@ -286,6 +287,14 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     int nproj = 0, bad = 0;
     T* const kl = ks + lane * 4;   // this lane's column inside every slot (see ks_load / ks_store)
 
+    // The reference tests every stage matrix against SO(3) before using it (state_decomposition inside EoM) and
+    // re-projects it if the test fails -- which, for stage points of an accepted-size step, essentially never
+    // happens.  The stages therefore run SPECULATIVELY: the test is evaluated as plain dataflow (nothing waits
+    // for it), and if some stage failed it the attempt is thrown away and redone by this lane in `checked` mode,
+    // where a failing stage is re-projected exactly like the reference does.  Same results as testing stage by
+    // stage, without a data-dependent branch per stage.
+    const bool checked = o.checked != 0;
+    bool all_ok = true;
 #pragma unroll 1
     for (int s = 1; s <= 11; ++s) {
         // ys = y + sum_j (h a_sj) K_j
@@ -307,16 +316,26 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
             axpy14<T>(c, k, ys);
         }
         const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
-        if (s >= 5) {
-            const T bs = TB::B(s), e5s = TB::E5(s), e3s = TB::E3(s);
+        {
+            const T bs = TB::B(s), e5s = TB::E5(s), e3s = TB::E3(s);   // zero for s < 5: no branch
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 xb[i] = N::fma(bs, ys[i], xb[i]); x5[i] = N::fma(e5s, ys[i], x5[i]); x3[i] = N::fma(e3s, ys[i], x3[i]);
             }
         }
+        const bool ok = so3_ok<T>(ys + 3);
+        all_ok = all_ok && ok;
+        if (checked && !ok) {   // slow path of a redone attempt: the reference's re-projection
+            T tmp[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) tmp[i] = ys[3 + i];
+            const int pb = project_so3<T>(tmp);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) ys[3 + i] = tmp[i];
+            nproj += 1; bad |= pb ? 2 : 0;
+        }
         T kn[14];
-        int fl = rhs14<T>(ys, W3s, d, kn);
-        nproj += fl & 1; bad |= fl & 2;
+        rhs14<T, false, false>(ys, W3s, d, kn);
         ks_store_lane<T>(kl + k_slot(s) * QR_SLOT_ELEMS, lane, kn);
     }
 
@@ -355,6 +374,8 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     else err = N::abs(h) * e5n * N::rsqrt((e5n + (T)0.01 * e3n) * (T)18);
 
     if (!live) return false;
+    if (!all_ok && !checked) { o.checked = 1; return false; }   // redo this attempt with per-stage re-projection
+    o.checked = 0;
     if (too_small) { o.status |= 2; return true; }
     o.h_abs = N::abs(h);
     o.nfev += 12;

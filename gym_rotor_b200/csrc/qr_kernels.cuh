@@ -29,6 +29,7 @@ template <typename T> struct StepArgs {
     int64_t env_lo, env_hi;    // range processed by this launch
     int64_t env_id_offset;     // global id of local env 0
     uint32_t key0, key1;       // Philox key = seed
+    unsigned long long* tile_counter;   // zeroed before every launch: next 32-env tile to hand out
     T *state, *integ, *params, *goal;
     T* traj;                   // [12][n] trajectory-generator state (goal modes hover / circle / eight)
     float* obs; T* reward; uint8_t *done, *terminated, *truncated; float* final_obs;
@@ -196,13 +197,14 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     if (lane < 16) ws[lane] = 0.0;
     __syncwarp();
 
-    // this warp's virtual env sequence
-    const int64_t gw = (int64_t)blockIdx.x * wpb + warp, W = (int64_t)gridDim.x * wpb;
+    // 32-env tiles are handed out dynamically (one atomic per tile on a per-launch counter): warps that drew
+    // cheap envs simply take more tiles, so the persistent grid drains evenly
+    (void)wpb;
     const int64_t n_range = a.env_hi - a.env_lo;
     const int64_t ntiles = (n_range + 31) >> 5;
-    const int64_t my_tiles = (ntiles > gw) ? (ntiles - gw + W - 1) / W : 0;
-    const int64_t vlen = my_tiles << 5;
-    int64_t cursor = 0;   // warp-uniform
+    int64_t tile_base = 0;    // warp-uniform: first env of the tile currently being handed out
+    int tile_pos = 32;        // warp-uniform: envs of that tile already taken (32 = none left)
+    bool exhausted = false;   // warp-uniform: the counter ran past the last tile
 
     // per-lane persistent state
     bool busy = false, fin = false, need_init = false;
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     T ep_ret[2] = {0, 0};
     int ep_len = 0;
     uint32_t ep_idx = 0;
+    T g_b1d[3] = {1, 0, 0}, g_Wd[3] = {0, 0, 0};   // mode-0 goal of the step in flight (xd = vd = 0): no reload at the end
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = 0;
 #pragma unroll
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 #pragma unroll
     for (int i = 0; i < 8; ++i) I[i] = 0;
     d.fm = d.g = d.Mi0 = d.Mi1 = d.kw0 = d.kw1 = d.w3dot = 0;
-    ode.t = 0; ode.h_abs = c.dt; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0;
+    ode.t = 0; ode.h_abs = c.dt; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0; ode.checked = 0;
 
     for (;;) {
         // =============================== phase A ===============================
@@ -247,8 +250,13 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 r.W3 = W3;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r.I[i] = I[i];
+                if (c.goal_mode == 1) {
 #pragma unroll
-                for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * N + e];
+                    for (int i = 0; i < 3; ++i) { r.goal[i] = 0; r.goal[3 + i] = 0; r.goal[6 + i] = g_b1d[i]; r.goal[9 + i] = g_Wd[i]; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * N + e];
+                }
                 double rew[2]; int dn[2];
                 if (MODE == 0) {
 #pragma unroll
@@ -408,13 +416,26 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         // ---- A2: idle lanes take the next envs of the warp's sequence ----
         {
             const unsigned need = __ballot_sync(FULL, !busy);
-            if (need && cursor < vlen) {
+            const int cnt = __popc(need);
+            if (cnt && !(exhausted && tile_pos >= 32)) {
                 const int rank = __popc(need & ((1u << lane) - 1u));
-                const int64_t v = cursor + rank;
-                cursor += __popc(need);
-                if (!busy && v < vlen) {
-                    const int64_t tile = gw + (v >> 5) * W;
-                    const int64_t ee = a.env_lo + (tile << 5) + (v & 31);
+                const int rem = 32 - tile_pos;
+                int64_t base2 = -1;
+                if (cnt > rem && !exhausted) {
+                    unsigned long long t = 0;
+                    if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
+                    t = __shfl_sync(FULL, t, 0);
+                    if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
+                    else exhausted = true;
+                }
+                int64_t ee = a.env_hi;
+                if (!busy) {
+                    if (rank < rem) ee = tile_base + tile_pos + rank;
+                    else if (base2 >= 0) ee = base2 + (rank - rem);
+                }
+                if (cnt > rem) { tile_base = base2; tile_pos = (base2 >= 0) ? cnt - rem : 32; }
+                else tile_pos += cnt;
+                {
                     if (ee < a.env_hi) {
                         e = ee; k = 0; busy = true; need_init = true;
 #pragma unroll
@@ -463,9 +484,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 #pragma unroll
                 for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
             }
-            // the observation at the end of this step reads xd, vd (goal rows 0-5): have them in L2 by then
+            if (c.goal_mode != 1) {   // the observation at the end of this step reads the goal: have it in L2 by then
 #pragma unroll
-            for (int i = 0; i < 6; ++i) prefetch_l2(a.goal + i * N + e);
+                for (int i = 0; i < 12; ++i) prefetch_l2(a.goal + i * N + e);
+            }
             if (!a.actions) {
                 const uint64_t gid = (uint64_t)(a.env_id_offset + e);
                 uint32_t rnd[8];
@@ -490,7 +512,11 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 T Wd[3];
                 traj_wd<T>(y + 3, Wv, b1d, Wd);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
+                for (int i = 0; i < 3; ++i) { g_b1d[i] = b1d[i]; g_Wd[i] = Wd[i]; }
+                if (k == a.n_steps - 1) {   // visible in the goal buffer like env.Wd after set_goal_state
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
+                }
             }
             T f, M[3];
             action_to_fM<T>(r, c, act, act_f32, f, M, MODE);

@@ -50,6 +50,7 @@ struct qr_handle {
     void* d_actions; size_t d_actions_bytes;
     double* d_stage; size_t d_stage_bytes;
     cudaStream_t io_stream;
+    unsigned long long* tile_counter;
     int num_sms; int smem_optin; int attr_set[2];
 };
 
@@ -94,6 +95,9 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     a.env_lo = lo; a.env_hi = hi;
     a.actions = actions; a.act_f32 = (act_dtype == QR_F32); a.n_steps = n_steps;
     a.obs_roll = obs_roll; a.reward_roll = (T*)reward_roll; a.done_roll = done_roll;
+    // launches on different streams (qr_step_host pipelines two) must not share a tile counter
+    a.tile_counter = h->tile_counter + ((s == h->io_stream) ? 1 : 0);
+    QR_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), s));
     // persistent warps: one CTA per SM, as many warps as the stage storage in shared memory allows
     const size_t per_warp = qr::warp_smem<T>::bytes;
     int warps = (int)((size_t)h->smem_optin / per_warp);
@@ -183,7 +187,8 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
         {(void**)&h->obs, n * h->O * 4}, {&h->reward, n * h->G * E}, {(void**)&h->done, n * h->G},
         {(void**)&h->terminated, n}, {(void**)&h->truncated, n}, {(void**)&h->final_obs, n * h->O * 4},
         {(void**)&h->nfev, n * 4}, {(void**)&h->status, n}, {&h->ep_return, 2 * n * E}, {(void**)&h->ep_length, n * 4},
-        {(void**)&h->ep_index, n * 4}, {(void**)&h->stats, QR_NUM_STATS * sizeof(double)}};
+        {(void**)&h->ep_index, n * 4}, {(void**)&h->stats, QR_NUM_STATS * sizeof(double)},
+        {(void**)&h->tile_counter, 2 * sizeof(unsigned long long)}};
     for (auto& al : allocs) {
         cudaError_t ce = cudaMalloc(al.p, al.bytes);
         if (ce != cudaSuccess) {
@@ -232,7 +237,7 @@ int qr_destroy(qr_handle* h)
 {
     if (!h) return QR_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->traj, h->state, h->integ, h->params, h->goal, h->obs, h->reward, h->done, h->terminated, h->truncated,
+    void* ptrs[] = {h->tile_counter, h->traj, h->state, h->integ, h->params, h->goal, h->obs, h->reward, h->done, h->terminated, h->truncated,
                     h->final_obs, h->nfev, h->status, h->ep_return, h->ep_length, h->ep_index, h->stats, h->d_actions, h->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->io_stream) cudaStreamDestroy(h->io_stream);
