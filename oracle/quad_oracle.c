@@ -40,6 +40,10 @@
 TAB(double, _f64)
 TAB(float, _f32)
 
+/* test instrumentation: SO(3) re-projections that happened inside DOP853 stages / f_new (not the Euler probe) */
+static long long qo_stage_projections = 0;
+long long qo_stage_projection_count(int reset) { long long v = qo_stage_projections; if (reset) qo_stage_projections = 0; return v; }
+
 /* ---- instantiate for double ------------------------------------------------------------------------ */
 #define REAL double
 #define RWD double
@@ -228,7 +232,7 @@ int qo_rhs_f64(int64_t n, const double* y, const double* params, const double* f
         rhs_par_f64 p;
         p.m = params[6 * e]; p.J1 = params[6 * e + 2]; p.J3 = params[6 * e + 3]; p.g = 9.81;
         p.f = fM[4 * e]; p.M[0] = fM[4 * e + 1]; p.M[1] = fM[4 * e + 2]; p.M[2] = fM[4 * e + 3];
-        p.n_svd = 0; p.svd_bad = 0;
+        p.n_svd = 0; p.svd_bad = 0; p.n_svd_stage = 0; p.in_probe = 0;
         rhs_f64(y + 18 * e, ydot + 18 * e, &p);
     }
     return 0;

@@ -65,6 +65,8 @@ def lib():
         L.qo_traj_desired_f64.argtypes = [C.c_int, C.c_int64, dp, dp, dp, dp, C.c_double]
         L.qo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.qo_set_threads.argtypes = [C.c_int]
+        L.qo_stage_projection_count.argtypes = [C.c_int]
+        L.qo_stage_projection_count.restype = C.c_longlong
         L.qo_get_max_threads.restype = C.c_int
         _lib = L
     return _lib

@@ -462,3 +462,28 @@ def test_trajectory_mode_autoreset_restarts_the_trajectory():
     assert eplen.max() <= 40 and np.abs(tclock - (1 + eplen) * 0.005).max() < 1e-6
     assert int(env.stats()[0]) >= n
     env.close()
+
+
+@pytest.mark.parametrize("scale", [20.0, 150.0])
+def test_extreme_angular_rates_exercise_stage_reprojection(scale):
+    """Far outside the termination limits (|W| <= 2 pi) DOP853 stage matrices do leave SO(3) by more than 1e-5 and
+    the reference re-projects them inside EoM.  The kernel runs its stages speculatively and redoes such an attempt
+    in checked mode: results and RHS counts must still equal the oracle's stage-by-stage evaluation."""
+    n = 2048
+    rng = np.random.default_rng(0)
+    orc = qo.COracle("MONO", threads=qo.lib().qo_get_max_threads())
+    st, ig, par = orc.reset_from_uniforms(rng.random((n, 20)))
+    st[:, 15:18] = rng.uniform(-scale, scale, (n, 3))
+    goal = np.zeros((n, 12)); goal[:, 6] = 1.0
+    act = rng.uniform(-1, 1, (n, 4))
+    env = _env(n, "MONO")
+    env.set_state(st, ig, par, goal)
+    qo.lib().qo_stage_projection_count(1)
+    o_ref, r_ref, d_ref, nfev, status = orc.step(st, ig, par, goal, act)
+    assert qo.lib().qo_stage_projection_count(1) > 100          # the slow path really is exercised
+    obs, rew, done, _, _ = env.step(_t(act, torch.float64))
+    sg, igg, _, _ = env.get_state()
+    assert (env.nfev.cpu().numpy() == nfev).all()
+    assert _relerr(sg, st) <= 1e-11 and np.abs(igg - ig).max() <= 1e-11
+    assert (done.cpu().numpy() == d_ref).all()
+    env.close()
