@@ -298,6 +298,49 @@ def time_limit_relabel(obs_n, reward, done, framework, x_lim=1.0):
     return out
 
 
+def forces_from_fM(f, M, d=0.23, c_tf=0.0135, min_force=None, max_force=None):
+    """(f, M) -> rotor thrusts T1..T4 = fM_to_forces @ [f; M] (the inverse of quad.py:396-401), optionally clipped
+    to [min_force, max_force] as draw_plot.py:55-72 does.  Diagnostic output only: the wrappers' dynamics never
+    clip individual rotor thrusts (coupled_yaw_wrapper.py:44-53)."""
+    f = torch.as_tensor(f, dtype=torch.float64); M = torch.as_tensor(M, dtype=torch.float64)
+    A = torch.tensor([[1.0, 1.0, 1.0, 1.0], [0.0, -d, 0.0, d], [d, 0.0, -d, 0.0], [-c_tf, c_tf, -c_tf, c_tf]],
+                     dtype=torch.float64, device=f.device)
+    fM = torch.cat([f.reshape(-1, 1), M.reshape(-1, 3)], dim=1)
+    T = fM @ torch.linalg.inv(A).T
+    if min_force is not None:
+        T = T.clamp(min=min_force)
+    if max_force is not None:
+        T = torch.minimum(T, torch.as_tensor(max_force, dtype=torch.float64, device=T.device).reshape(-1, 1))
+    return T
+
+
+class FlightLog:
+    """The evaluation flight log of main.py:344-352,382-389 for ONE env of a batch: per step a row
+    `action | state[18] | eIx[3] | eb1 | eIb1 | xd[3] | vd[3] | b1d[3] | Wd[3]` (39 columns MONO, 40 MODUL), written with
+    %.10f under the reference's two header lines, so that draw_plot.py reads it unchanged."""
+
+    def __init__(self, env, index=0):
+        self.env, self.i, self.rows = env, index, []
+
+    def record(self, action, obs_n):
+        e, i = self.env, self.i
+        o = [t[i].double().cpu().numpy() for t in obs_n]
+        if e.framework == "MODUL":
+            eIx, eb1, eIb1 = o[0][3:6] * e.eIx_lim, o[1][0] * np.pi, o[1][1] * e.eIb1_lim
+        else:
+            eIx, eb1, eIb1 = o[0][3:6] * e.eIx_lim, o[0][18] * np.pi, o[0][19] * e.eIb1_lim
+        st = e.state_soa[:, i].double().cpu().numpy()
+        gl = e.goal_soa[:, i].double().cpu().numpy()
+        act = action[i].double().cpu().numpy().ravel()
+        self.rows.append(np.concatenate([act, st, eIx, [eb1], [eIb1], gl]))
+
+    def save(self, path):
+        with open(path, "w") as f:
+            f.write("# Actions and States\n# action[0], ..., state[0], ..., command[0], ...\n")
+            for r in self.rows:
+                f.write(" ".join("%.10f" % v for v in r) + "\n")
+
+
 class QuadVectorEnv:
     """gymnasium.vector.VectorEnv-shaped facade (gymnasium itself is not installed in this image).
 

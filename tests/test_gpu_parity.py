@@ -487,3 +487,38 @@ def test_extreme_angular_rates_exercise_stage_reprojection(scale):
     assert _relerr(sg, st) <= 1e-11 and np.abs(igg - ig).max() <= 1e-11
     assert (done.cpu().numpy() == d_ref).all()
     env.close()
+
+
+def test_cabi_error_paths_and_independent_handles():
+    """int return codes + qr_last_error instead of exceptions; two handles on one device do not interact."""
+    import ctypes as C
+    from gym_rotor_b200 import _native as nat
+    L = nat.load()
+    cfg = nat.QrConfig(); assert L.qr_default_config(C.byref(cfg), nat.MODE_COUPLED, nat.F32) == 0
+    h = C.c_void_p()
+    cfg.n_envs = 0
+    assert L.qr_create(C.byref(cfg), 0, C.byref(h)) == 1 and b"n_envs" in L.qr_last_error()
+    cfg.n_envs = 64; cfg.integrator = nat.INT_EULER
+    assert L.qr_create(C.byref(cfg), 0, C.byref(h)) == 1 and b"Euler" in L.qr_last_error()
+    cfg.integrator = nat.INT_DOP853
+    assert L.qr_create(C.byref(cfg), 99, C.byref(h)) == 1 and b"device" in L.qr_last_error()
+    assert L.qr_create(C.byref(cfg), 0, C.byref(h)) == 0
+    assert L.qr_step(h, None, nat.F32, None) == 1 and b"null actions" in L.qr_last_error()
+    act = torch.zeros((64, 4), device="cuda:0")
+    assert L.qr_step(h, C.c_void_p(act.data_ptr()), 7, None) == 1
+    assert L.qr_rollout(h, 0, None, nat.F32, None, None, None, None) == 1
+    assert L.qr_stats(h, None, 0, None) == 1
+    assert L.qr_step(None, C.c_void_p(act.data_ptr()), nat.F32, None) == 1
+    assert L.qr_destroy(h) == 0 and L.qr_destroy(None) == 0
+    # two independent handles, interleaved on different streams
+    a = _env(512, "MONO", torch.float32, seed=1); b = _env(512, "MONO", torch.float32, seed=1)
+    a.reset(); b.reset()
+    act = torch.rand((512, 4), device="cuda:0") * 2 - 1
+    s1 = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        a.step(act)
+    b.step(act)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state_soa, b.state_soa) and torch.equal(a.obs, b.obs)
+    a.close(); b.close()

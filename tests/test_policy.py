@@ -117,3 +117,47 @@ def test_trainer_side_helpers_match_reference_formulas():
     o1 = torch.as_tensor(obs[:, :15]); o2 = torch.as_tensor(obs[:, 15:18])
     refm = np.interp(-np.linalg.norm(ex, axis=1) - np.abs(obs[:, 15].astype(np.float64) * np.pi), [-2., 0.], [0., 1.])
     assert np.abs(benchmark_reward([o1, o2], "MODUL").numpy() - refm).max() < 1e-12
+
+
+def test_forces_from_fM_inverts_the_mixing_matrix():
+    """(f, M) -> T1..T4 diagnostic (draw_plot.py:55-72): inverse of forces_to_fM (quad.py:396-401)."""
+    from gym_rotor_b200.vec_env import forces_from_fM
+    rng = np.random.default_rng(1)
+    T = rng.uniform(0.5, 11.0, (50, 4)); d, c = 0.23, 0.0135
+    A = np.array([[1, 1, 1, 1], [0, -d, 0, d], [d, 0, -d, 0], [-c, c, -c, c]], float)
+    fM = T @ A.T
+    out = forces_from_fM(fM[:, 0], fM[:, 1:4]).numpy()
+    assert np.abs(out - T).max() < 1e-10
+    clipped = forces_from_fM(fM[:, 0], fM[:, 1:4], min_force=2.0, max_force=8.0).numpy()
+    assert clipped.min() >= 2.0 and clipped.max() <= 8.0
+
+
+@pytest.mark.gpu
+def test_flight_log_has_the_reference_layout(tmp_path):
+    """FlightLog writes rows that reproduce the reference's own .dat (KAT-1) when fed the same flight."""
+    from gym_rotor_b200 import vec_env
+    rows = np.load(os.path.join(G, "kat1_modul_log.npz"))["rows"]
+    env = vec_env.BatchedQuadEnv(2, framework="MODUL", dtype=torch.float64)
+    par = np.tile(np.array([2.15, 0.23, 0.022, 0.035, 0.0135, 2.2]), (2, 1))
+    log = vec_env.FlightLog(env, index=1)
+    H = 40
+    goal = np.tile(rows[0, 28:40], (2, 1))
+    integ = np.zeros((2, 8)); integ[:, 0:3] = rows[0, 23:26]; integ[:, 6] = rows[0, 27]
+    env.set_state(np.tile(rows[0, 5:23], (2, 1)), integ, par, goal)
+    for t in range(H):
+        act = torch.as_tensor(np.tile(rows[t, 0:5], (2, 1)), device="cuda:0")
+        g = np.tile(rows[t, 28:40], (2, 1))
+        env.set_state(None, None, None, g)
+        # the reference logs the PRE-step state with the action it is about to apply (main.py:344-352)
+        obs_pre = [env.obs[:, :15].clone(), env.obs[:, 15:18].clone()] if t else None
+        if t:
+            log.record(act, obs_pre)
+        env.step(act)
+    p = tmp_path / "log.dat"
+    log.save(str(p))
+    out = np.loadtxt(str(p))
+    assert out.shape == (H - 1, 40)
+    assert np.abs(out[:, 0:5] - rows[1:H, 0:5]).max() < 1e-9            # actions
+    assert np.abs(out[:, 5:23] - rows[1:H, 5:23]).max() < 5e-9          # states follow the logged flight
+    assert np.abs(out[:, 28:40] - rows[1:H, 28:40]).max() < 1e-9        # commands
+    env.close()
