@@ -142,6 +142,14 @@ template <> QR_DEV void axpy14<float>(float c, const float* k, float* acc)
         acc[2 * i] = r.x; acc[2 * i + 1] = r.y;
     }
 }
+// out[0..13] = base[0..13] + c * k[0..13]   (out of place: no copy of `base` first)
+template <typename T> QR_DEV void axpy14_out(T c, const T* k, const T* base, T* out)
+{
+#pragma unroll
+    for (int i = 0; i < 14; ++i) out[i] = num<T>::fma(c, k[i], base[i]);
+}
+// (no packed specialisation: `base` is the persistent state, whose registers are not pair-aligned -- packing
+//  it costs one MOV per element, more than the FFMA2 saves; the results land directly in the pair-aligned `out`)
 // three weighted sums at once (y_new and the two error estimators)
 template <typename T> QR_DEV void axpy14x3(T b, T e5, T e3, const T* k, T* sb, T* s5, T* s3)
 {
@@ -301,9 +309,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         T ys[14];
         {
             const T ha0 = h * TB::A(s, 0);
-#pragma unroll
-            for (int i = 0; i < 14; ++i) ys[i] = y[i];
-            axpy14<T>(ha0, K0, ys);
+            axpy14_out<T>(ha0, K0, y, ys);
         }
         const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
         // (measured and dropped: two K vectors per trip / software pipelining -- the extra registers cost more
