@@ -28,7 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 ALG_BYTES = {"MONO_f32": 366, "MONO_f64": 614, "MODUL_f32": 363}   # SURVEY 8(d), per env-step
 ALG_FLOPS = 5450                                                   # SURVEY 8(d), one DOP853 attempt
 STATS_EVERY = 128
-DRAM_BYTES_PER_ENV_STEP_NCU = 417.3   # ncu --set full capture r01k: 875.2 MB per launch of 2^21 env-steps
+DRAM_BYTES_PER_ENV_STEP_NCU = 388.6   # ncu --set full capture r01m: 814.9 MB per launch of 2^21 env-steps
 
 
 def _peaks():
