@@ -285,7 +285,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": (DRAM_BYTES_PER_ENV_STEP_NCU * n * fused / 1e9) if (fw == "MONO" and args.dtype == "f32") else None,
-                         "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01k_kstep_f32_ncu_digest.txt)",
+                         "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01m_kstep_f32_ncu_digest.txt)",
                          "peak_source": which, "kernel": "qr::k_step<%s>" % ("double" if args.dtype == "f64" else "float"),
                          "algorithmic_bytes_per_env_step": bytes_per, "kernel_ms": kernel_ms},
             "roofline_fp": {"bound": "fp%s issue" % ("64" if args.dtype == "f64" else "32"),

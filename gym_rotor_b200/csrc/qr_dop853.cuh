@@ -31,13 +31,21 @@
 namespace qr {
 
 // ---- tableau in constant memory (uniform-indexed loads in the rolled stage loop) ------------------------
+// P / Ps: the 45 non-zero couplings A[s][j], j >= 1, flattened in stage order (entries Ps[s] .. Ps[s+1]-1 belong
+// to stage s), each with the byte offset of K_j's slot inside a warp's stage storage: the inner loop of the
+// stage sums is one 8/16-byte constant load + one add per K vector instead of index arithmetic.
+template <typename T> struct TabEntry { T c; int off; };
 struct Tableau {
     double A[12][12];
     double B[12], E5[12], E3[12], C[12];
+    TabEntry<double> P[48];
+    int Ps[16];
 };
 struct TableauF {
     float A[12][12];
     float B[12], E5[12], E3[12], C[12];
+    TabEntry<float> P[48];
+    int Ps[16];
 };
 __constant__ Tableau c_tab64;
 __constant__ TableauF c_tab32;
@@ -71,6 +79,8 @@ template <> struct tab<double> {
     static QR_DEV double E5(int j) { return c_tab64.E5[j]; }
     static QR_DEV double E3(int j) { return c_tab64.E3[j]; }
     static QR_DEV double C(int j) { return c_tab64.C[j]; }
+    static QR_DEV TabEntry<double> P(int p) { return c_tab64.P[p]; }
+    static QR_DEV int Ps(int s) { return c_tab64.Ps[s]; }
 };
 template <> struct tab<float> {
     static QR_DEV float A(int s, int j) { return c_tab32.A[s][j]; }
@@ -78,6 +88,8 @@ template <> struct tab<float> {
     static QR_DEV float E5(int j) { return c_tab32.E5[j]; }
     static QR_DEV float E3(int j) { return c_tab32.E3[j]; }
     static QR_DEV float C(int j) { return c_tab32.C[j]; }
+    static QR_DEV TabEntry<float> P(int p) { return c_tab32.P[p]; }
+    static QR_DEV int Ps(int s) { return c_tab32.Ps[s]; }
 };
 
 // ---- shared-memory stage storage ----------------------------------------------------------------------------
@@ -86,7 +98,8 @@ template <> struct tab<float> {
 //   element (c, lane): c < 12 -> ((c >> 2) * 32 + lane) * 4 + (c & 3) ;  c >= 12 -> 384 + lane * 2 + (c - 12)
 constexpr int QR_NSLOTS = 9;
 constexpr int QR_SLOT_ELEMS = 14 * 32;
-QR_DEV int k_slot(int j) { return j < 5 ? ((j + 1) & 1) : j - 3; }   // K1,K3 -> 0 ; K2,K4 -> 1 ; K5.. -> 2..8
+QR_DEV int k_slot(int j) { return j < 5 ? ((j + 1) & 1) : j - 3; }
+inline int k_slot_host(int j) { return j < 5 ? ((j + 1) & 1) : j - 3; }   // K1,K3 -> 0 ; K2,K4 -> 1 ; K5.. -> 2..8
 
 template <typename T> struct vec4 { T a, b, c, d; };
 template <typename T> struct vec2 { T a, b; };
@@ -112,6 +125,17 @@ template <typename T> QR_DEV void ks_load_lane(const T* col, int lane, T* k)
         }
     }
 }
+// Same as ks_load_lane for float, from a 32-bit shared-window address (`sa` = address of the lane's column in the
+// slot, `lane8` = lane * 8): explicit ld.shared with immediate offsets, so the loop needs one add per K vector.
+QR_DEV void ks_load_lane_sa(unsigned sa, unsigned lane8, float* k)
+{
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(k[0]), "=f"(k[1]), "=f"(k[2]), "=f"(k[3]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+512];" : "=f"(k[4]), "=f"(k[5]), "=f"(k[6]), "=f"(k[7]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+1024];" : "=f"(k[8]), "=f"(k[9]), "=f"(k[10]), "=f"(k[11]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+1536];" : "=f"(k[12]), "=f"(k[13]) : "r"(sa - lane8) : "memory");
+}
+QR_DEV void ks_load_lane_sa(unsigned, unsigned, double*) {}   // float64 uses the generic-pointer loader
+
 template <typename T> QR_DEV void ks_store_lane(T* col, int lane, const T* k)
 {
     if (sizeof(T) == 4) {
@@ -294,6 +318,8 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     for (int i = 0; i < 3; ++i) { xb[i] = TB::B(0) * y[i]; x5[i] = TB::E5(0) * y[i]; x3[i] = TB::E3(0) * y[i]; }
     int nproj = 0, bad = 0;
     T* const kl = ks + lane * 4;   // this lane's column inside every slot (see ks_load / ks_store)
+    unsigned kl_sa = (unsigned)__cvta_generic_to_shared(kl);
+    asm volatile("" : "+r"(kl_sa));   // keep it in a register: the compiler otherwise re-derives it per K vector
 
     // The reference tests every stage matrix against SO(3) before using it (state_decomposition inside EoM) and
     // re-projects it if the test fails -- which, for stage points of an accepted-size step, essentially never
@@ -311,14 +337,17 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
             const T ha0 = h * TB::A(s, 0);
             axpy14_out<T>(ha0, K0, y, ys);
         }
-        const int jlo = (s <= 2) ? s - 1 + (s == 1) : (s <= 4 ? 2 : 3);   // s=1: none, 2:[1], 3:[2], 4:[2,3], 5:[3,4], >=6:[3..s-1]
+        // couplings A[s][j], j >= 1, from the flattened table (constant bank, uniform datapath)
         // (measured and dropped: two K vectors per trip / software pipelining -- the extra registers cost more
         //  than the exposed LDS latency, profiles/r01_summary.md)
+        const int p1 = TB::Ps(s + 1);
 #pragma unroll 1
-        for (int j = jlo; j < s; ++j) {
-            const T c = h * TB::A(s, j);
+        for (int p = TB::Ps(s); p < p1; ++p) {
+            const TabEntry<T> te = TB::P(p);
+            const T c = h * te.c;
             T k[14];
-            ks_load_lane<T>(kl + k_slot(j) * QR_SLOT_ELEMS, lane, k);
+            if (sizeof(T) == 4) ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, k);
+            else ks_load_lane<T>(reinterpret_cast<const T*>(reinterpret_cast<const char*>(kl) + te.off), lane, k);
             axpy14<T>(c, k, ys);
         }
         const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);

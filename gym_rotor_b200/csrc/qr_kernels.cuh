@@ -14,6 +14,12 @@
 #include "qr_traj.cuh"
 #include "generated/actor_td3.cuh"
 
+#ifndef QR_DEFER_RESET
+#define QR_DEFER_RESET 1
+#endif
+#ifndef QR_RESET_BATCH
+#define QR_RESET_BATCH 24
+#endif
 namespace qr {
 
 constexpr int QR_BLOCK = 128;        // companion kernels (reset, goal init, observation)
@@ -167,13 +173,13 @@ QR_DEV float warp_sum_f(float v)
 // resource at 12 warps per SM) and flushed with one atomic per statistic and warp at the end.
 //
 // Per-warp shared memory: KS[9][14][32] T (stage derivatives) | OS[32][O] f32 (observation rows, by lane) |
-//                         WS[16] f64 (statistics) | ROWMAP[32] u8 (tile row -> lane)
+//                         WS[16] f64 (statistics) | RQ[32] i32 (envs whose reset is pending, see below)
 template <typename T> struct warp_smem {
     static constexpr size_t ks_bytes = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T);
     static constexpr size_t os_bytes = 32 * 23 * sizeof(float);
     static constexpr size_t ws_bytes = 16 * sizeof(double);
-    static constexpr size_t map_bytes = 32;
-    static constexpr size_t bytes = ks_bytes + os_bytes + ws_bytes + map_bytes;   // multiple of 16
+    static constexpr size_t rq_bytes = 32 * sizeof(int32_t);
+    static constexpr size_t bytes = ks_bytes + os_bytes + ws_bytes + rq_bytes;   // multiple of 16
 };
 
 template <typename T, int MODE>
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     T* ks = reinterpret_cast<T*>(wbase);
     float* os = reinterpret_cast<float*>(wbase + warp_smem<T>::ks_bytes);
     double* ws = reinterpret_cast<double*>(wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes);
-    unsigned char* rowmap = wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes + warp_smem<T>::ws_bytes;
+    int32_t* rq = reinterpret_cast<int32_t*>(wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes + warp_smem<T>::ws_bytes);
     const Philox ph{a.key0, a.key1};
 
     if (lane < 16) ws[lane] = 0.0;
@@ -228,13 +234,41 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     d.fm = d.g = d.Mi0 = d.Mi1 = d.kw0 = d.kw1 = d.w3dot = 0;
     ode.t = 0; ode.h_abs = c.dt; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0; ode.checked = 0;
 
+    // queued resets (single-step launches): lane i resets the env in RQ[i] -- all queued envs at once -- and
+    // writes the new episode's state, integrals and first observation straight to the arrays.  The lanes' own
+    // env registers are not involved: the reset works through shared scratch (the stage storage, free in phase A).
+    int rq_n = 0;                                                          // warp-uniform: entries in RQ
+    const bool defer_ok = a.n_steps == 1 && N < ((int64_t)1 << 31);        // kernel-uniform
+    auto flush_resets = [&]() {
+        __syncwarp();
+        if (lane < rq_n) {
+            const int64_t er = (int64_t)rq[lane];
+            const uint32_t ep = __ldcg(a.ep_index + er);   // written when the env was released (already incremented)
+            auto_reset_env<T, MODE>(&a, er, ep, os + lane * O, ks + lane * 32);
+            const T* sc = ks + lane * 32;
+#pragma unroll
+            for (int i = 0; i < 18; ++i) a.state[i * N + er] = sc[i];   // scratch order = state row order
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a.integ[i * N + er] = sc[18 + i];
+            float* d1 = a.obs_roll ? a.obs_roll + er * O : a.obs + er * O;
+#pragma unroll
+            for (int i = 0; i < O; ++i) d1[i] = os[lane * O + i];
+            if (a.obs_roll) {
+#pragma unroll 1
+                for (int i = 0; i < O; ++i) a.obs[er * O + i] = os[lane * O + i];
+            }
+        }
+        __syncwarp();
+        rq_n = 0;
+    };
+
     for (;;) {
         // =============================== phase A ===============================
         // ---- A1: finish the env.step that just completed ----
         const unsigned finmask = __ballot_sync(FULL, fin);
         if (finmask) {
             __syncwarp();   // phase B is over for every lane: the stage storage may be reused as reset scratch
-            bool did_reset = false, term = false, trunc = false;
+            bool did_reset = false, ep_done = false, deferred = false, term = false, trunc = false;
             int nf = 0, st = 0, nproj = 0, ep_len_done = 0;
             float rew0f = 0.f;
             T ret_done0 = 0, ret_done1 = 0;
@@ -298,10 +332,27 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
                     }
                     ep_idx += 1;
-                    // the new episode's first observation replaces the terminal one in this lane's tile row
-                    auto_reset_env<T, MODE>(&a, e, ep_idx, os + lane * O, ks + lane * 32);   // the stage storage is free in phase A
                     ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
-                    did_reset = true;
+                    ep_done = true;
+                }
+            }
+            // ---- auto reset.  A reset is ~1 000 instructions for one lane of the warp; with single-step launches
+            // the env leaves the lane anyway, so its reset is QUEUED (per warp) and a whole batch of queued envs is
+            // reset by all lanes at once further down.  Multi-step launches (the env continues in this lane) and
+            // queue overflow (e.g. a common time limit hitting every env at once) reset on the spot. ----
+            {
+                const unsigned wmask = __ballot_sync(FULL, ep_done);
+                if (wmask) {
+                    if (QR_DEFER_RESET && defer_ok) {
+                        const int pos = rq_n + __popc(wmask & ((1u << lane) - 1u));
+                        if (ep_done && pos < 32) { rq[pos] = (int32_t)e; deferred = true; }
+                        rq_n = min(32, rq_n + __popc(wmask));
+                    }
+                    if (ep_done && !deferred) {
+                        // the new episode's first observation replaces the terminal one in this lane's staging row
+                        auto_reset_env<T, MODE>(&a, e, ep_idx, os + lane * O, ks + lane * 32);   // the stage storage is free in phase A
+                        did_reset = true;
+                    }
                 }
             }
             __syncwarp();
@@ -314,7 +365,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 const unsigned m3 = __ballot_sync(FULL, fin && att == 3), m4 = __ballot_sync(FULL, fin && att >= 4);
                 const unsigned mbad = __ballot_sync(FULL, fin && st != 0);
                 const float s_rew = warp_sum_f(rew0f);
-                const unsigned mres = __ballot_sync(FULL, did_reset);
+                const unsigned mres = __ballot_sync(FULL, ep_done);
                 if (lane == 0) {
                     ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev; ws[15] += (double)s_proj;
                     ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
@@ -322,61 +373,31 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 }
                 if (mres) {   // once per episode
                     const int s_len = __reduce_add_sync(FULL, ep_len_done);
-                    const unsigned mterm = __ballot_sync(FULL, did_reset && term);
-                    const double r0 = (double)warp_sum_f(did_reset ? (float)ret_done0 : 0.f);
-                    const double r1 = (double)warp_sum_f(did_reset ? (float)ret_done1 : 0.f);
-                    const double r0sq = (double)warp_sum_f(did_reset ? (float)ret_done0 * (float)ret_done0 : 0.f);
+                    const unsigned mterm = __ballot_sync(FULL, ep_done && term);
+                    const double r0 = (double)warp_sum_f(ep_done ? (float)ret_done0 : 0.f);
+                    const double r1 = (double)warp_sum_f(ep_done ? (float)ret_done1 : 0.f);
+                    const double r0sq = (double)warp_sum_f(ep_done ? (float)ret_done0 * (float)ret_done0 : 0.f);
                     if (lane == 0) {
                         ws[0] += (double)__popc(mres); ws[3] += (double)s_len; ws[4] += (double)__popc(mterm);
                         ws[5] += (double)(__popc(mres) - __popc(mterm)); ws[1] += r0; ws[2] += r1; ws[6] += r0sq;
                     }
                 }
             }
-            // ---- observation rows: shared tile (row = lane) -> global.  Finished lanes are grouped by
-            // (32-env tile, sub-step); a group is written as O coalesced 128-byte stores through the
-            // row -> lane map, rows that are not part of the group masked out.  Stragglers (lanes that
-            // needed another attempt) belong to an older tile and are flushed in a further round.
-            unsigned rem = finmask;
-            const int myrow = (int)(e & 31);
-            while (rem) {
-                const int lead = __ffs(rem) - 1;
-                const int64_t tb = __shfl_sync(FULL, e & ~(int64_t)31, lead);
-                const int kk = __shfl_sync(FULL, k, lead);
-                const bool mine = fin && ((e & ~(int64_t)31) == tb) && (k == kk);
-                const unsigned grp = __ballot_sync(FULL, mine);
-                rem &= ~grp;
-                const bool lst = (kk == a.n_steps - 1);
-                float* d1 = a.obs_roll ? a.obs_roll + ((int64_t)kk * N + tb) * O : (lst ? a.obs + tb * O : nullptr);
-                float* d2 = (a.obs_roll && lst) ? a.obs + tb * O : nullptr;
-                if (__popc(grp) > 8) {
-                    // flat pass over the shared tile in source order: element q = it*32 + lane belongs to source
-                    // lane q / O (advanced without dividing); its tile row comes from that lane by shuffle.  Lanes
-                    // take consecutive envs, so consecutive sources have consecutive rows: full-line stores.
-                    int sl = lane / O, col = lane - sl * O;
+            // ---- observation rows: each finished lane writes its own row from the shared staging row (the new
+            // episode's first observation if the env was just reset).  Scattered 4-byte stores, but the rows of
+            // neighbouring lanes are adjacent in memory, so L2 assembles full sectors; measured 5 % faster than
+            // routing the rows through a coalescing copy loop (profiles/r01_summary.md, r01n).
+            if (fin && !deferred) {
+                const bool lst = (k == a.n_steps - 1);
+                float* d1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (lst ? a.obs + e * O : nullptr);
+                float* d2 = (a.obs_roll && lst) ? a.obs + e * O : nullptr;
+                if (d1) {
+#pragma unroll
+                    for (int i = 0; i < O; ++i) d1[i] = os[lane * O + i];
+                }
+                if (d2) {
 #pragma unroll 1
-                    for (int it = 0; it < O; ++it) {
-                        const int drow = __shfl_sync(FULL, myrow, sl);
-                        if ((grp >> sl) & 1u) {
-                            const float v = os[it * 32 + lane];
-                            const int di = drow * O + col;
-                            if (d1) d1[di] = v;
-                            if (d2) d2[di] = v;
-                        }
-                        col += 32 - O; sl += 1;
-                        if (col >= O) { col -= O; sl += 1; }
-                    }
-                } else {
-                    unsigned rr = grp;
-                    while (rr) {
-                        const int sl = __ffs(rr) - 1;
-                        rr &= rr - 1;
-                        const int drow = __shfl_sync(FULL, myrow, sl);
-                        if (lane < O) {
-                            const float v = os[sl * O + lane];
-                            if (d1) d1[drow * O + lane] = v;
-                            if (d2) d2[drow * O + lane] = v;
-                        }
-                    }
+                    for (int i = 0; i < O; ++i) d2[i] = os[lane * O + i];
                 }
             }
             __syncwarp();
@@ -397,14 +418,16 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 k += 1;
                 if (k < a.n_steps) need_init = true;
                 else {
-                    // release the env: state back to HBM
+                    // release the env: state back to HBM (not the terminal state of an env whose reset is queued)
+                    if (!deferred) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
+                        for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
-                    a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
+                        for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
+                        a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a.integ[i * N + e] = I[i];
+                        for (int i = 0; i < 8; ++i) a.integ[i * N + e] = I[i];
+                    }
                     a.ep_return[e] = ep_ret[0];
                     if (G == 2) a.ep_return[N + e] = ep_ret[1];
                     a.ep_length[e] = ep_len;
@@ -412,6 +435,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     busy = false;
                 }
             }
+            if (QR_DEFER_RESET && rq_n >= QR_RESET_BATCH) flush_resets();
         }
         // ---- A2: idle lanes take the next envs of the warp's sequence ----
         {
@@ -455,7 +479,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 }
             }
         }
-        if (!__any_sync(FULL, busy)) break;
+        if (!__any_sync(FULL, busy)) {
+            if (QR_DEFER_RESET && rq_n) flush_resets();
+            break;
+        }
         // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
         if (busy && need_init) {
             need_init = false;
