@@ -93,13 +93,14 @@ template <> struct tab<float> {
 };
 
 // ---- shared-memory stage storage ----------------------------------------------------------------------------
-// Per warp: KS[slot 0..8][14 components][32 lanes] of T.  Within a slot the 14 components of one lane are
+// Per warp: KS[slot 0..7][14 components][32 lanes] of T.  Within a slot the 14 components of one lane are
 // packed as 3 x (4 consecutive T) + 1 x (2 consecutive T) so that float accesses are LDS/STS.128 + .64:
 //   element (c, lane): c < 12 -> ((c >> 2) * 32 + lane) * 4 + (c & 3) ;  c >= 12 -> 384 + lane * 2 + (c - 12)
-constexpr int QR_NSLOTS = 9;
+constexpr int QR_NSLOTS = 8;
 constexpr int QR_SLOT_ELEMS = 14 * 32;
-QR_DEV int k_slot(int j) { return j < 5 ? ((j + 1) & 1) : j - 3; }
-inline int k_slot_host(int j) { return j < 5 ? ((j + 1) & 1) : j - 3; }   // K1,K3 -> 0 ; K2,K4 -> 1 ; K5.. -> 2..8
+QR_DEV int k_slot(int j) { return j < 5 ? ((j + 1) & 1) : (j == 11 ? 0 : j - 3); }
+inline int k_slot_host(int j) { return j < 5 ? ((j + 1) & 1) : (j == 11 ? 0 : j - 3); }
+// K1,K3 -> 0 ; K2,K4 -> 1 ; K5..K10 -> 2..7 ; K11 -> 0 again (K3 is last read by the stage that produces K11)
 
 template <typename T> struct vec4 { T a, b, c, d; };
 template <typename T> struct vec2 { T a, b; };
@@ -385,7 +386,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     for (int j = 5; j <= 11; ++j) {
         const T bj = TB::B(j), e5j = TB::E5(j), e3j = TB::E3(j);
         T k[14];
-        ks_load_lane<T>(kl + (j - 3) * QR_SLOT_ELEMS, lane, k);
+        ks_load_lane<T>(kl + (j == 11 ? 0 : j - 3) * QR_SLOT_ELEMS, lane, k);
         axpy14x3<T>(bj, e5j, e3j, k, sb, s5, s3);
     }
     T e5n = 0, e3n = 0;

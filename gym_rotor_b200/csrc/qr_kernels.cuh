@@ -14,9 +14,6 @@
 #include "qr_traj.cuh"
 #include "generated/actor_td3.cuh"
 
-#ifndef QR_DEFER_RESET
-#define QR_DEFER_RESET 1
-#endif
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
@@ -88,6 +85,16 @@ template <typename T> QR_DEV void store_params_goal(const EnvRegs<T>& r, const S
 
 QR_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// global -> shared without a register in between (LDGSTS); completion is awaited by the issuing thread
+template <int BYTES> QR_DEV void cp_async(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "n"(BYTES) : "memory");
+}
+template <typename T> QR_DEV int32_t& stash_i32(T* sh, int slot) { return *reinterpret_cast<int32_t*>(sh + slot * 32); }
+QR_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+QR_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> QR_DEV void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 QR_DEV double warp_sum(double v)
 {
 #pragma unroll
@@ -98,9 +105,9 @@ QR_DEV double warp_sum(double v)
 // ---- auto reset, out of line (rare: once per episode) ---------------------------------------------------------
 // env.reset -> trajectory_generator.mark_traj_start/get_desired -> set_goal_state -> get_norm_error_state
 // (main.py:226-230).  Works through global memory so that the hot loop's registers are not affected; the
-// caller re-loads the env afterwards.  `o` receives the first observation of the new episode.
+// caller re-loads the env afterwards.  `orow` (and `orow2`) receive the first observation of the new episode.
 template <typename T, int MODE>
-__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* orow, T* scratch)
+__device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, uint32_t episode, float* orow, float* orow2, T* scratch)
 {
     const StepArgs<T>& a = *ap;
     constexpr int O = (MODE == 1) ? 23 : 18;
@@ -145,7 +152,11 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
     scratch[26] = r.m; scratch[27] = r.d; scratch[28] = r.J1; scratch[29] = r.J3; scratch[30] = r.c_tf; scratch[31] = r.c_tw;
     store_params_goal(r, a, e, true, c.goal_mode >= 1);
 #pragma unroll
-    for (int i = 0; i < O; ++i) orow[i] = o[i];   // replaces the terminal observation in the caller's tile row
+    for (int i = 0; i < O; ++i) orow[i] = o[i];   // replaces the terminal observation of the step that ended the episode
+    if (orow2) {
+#pragma unroll 1
+        for (int i = 0; i < O; ++i) orow2[i] = o[i];
+    }
 }
 
 QR_DEV float warp_sum_f(float v)
@@ -172,17 +183,19 @@ QR_DEV float warp_sum_f(float v)
 // warp votes / REDUX into per-warp shared accumulators (no per-lane counters: registers are the scarce
 // resource at 12 warps per SM) and flushed with one atomic per statistic and warp at the end.
 //
-// Per-warp shared memory: KS[9][14][32] T (stage derivatives) | OS[32][O] f32 (observation rows, by lane) |
-//                         WS[16] f64 (statistics) | RQ[32] i32 (envs whose reset is pending, see below)
+// Per-warp shared memory: KS[8][14][32] T (stage derivatives) | STASH[36][32] T (per-lane values that are only needed
+//                         when a step ends: integrals, goal, episode counters; and the landing zone of the next
+//                         env's action / parameters / goal, fetched ahead) | WS[16] f64 (statistics) |
+//                         RQ[32] i32 (envs whose reset is pending, see below)
 template <typename T> struct warp_smem {
     static constexpr size_t ks_bytes = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T);
-    static constexpr size_t os_bytes = 32 * 23 * sizeof(float);
+    static constexpr size_t os_bytes = 32 * 36 * sizeof(T);   // the stash: 36 slots per lane
     static constexpr size_t ws_bytes = 16 * sizeof(double);
-    static constexpr size_t rq_bytes = 32 * sizeof(int32_t);
+    static constexpr size_t rq_bytes = 64 * sizeof(int32_t);
     static constexpr size_t bytes = ks_bytes + os_bytes + ws_bytes + rq_bytes;   // multiple of 16
 };
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool MULTI>
 __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid_constant__ StepArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     const int64_t N = a.n;
     unsigned char* wbase = smem_raw + warp * warp_smem<T>::bytes;
     T* ks = reinterpret_cast<T*>(wbase);
-    float* os = reinterpret_cast<float*>(wbase + warp_smem<T>::ks_bytes);
+    T* const sh = reinterpret_cast<T*>(wbase + warp_smem<T>::ks_bytes) + lane;   // stash slot j of this lane: sh[j * 32]
     double* ws = reinterpret_cast<double*>(wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes);
     int32_t* rq = reinterpret_cast<int32_t*>(wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes + warp_smem<T>::ws_bytes);
     const Philox ph{a.key0, a.key1};
@@ -212,70 +225,106 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     int tile_pos = 32;        // warp-uniform: envs of that tile already taken (32 = none left)
     bool exhausted = false;   // warp-uniform: the counter ran past the last tile
 
-    // per-lane persistent state
+    // per-lane persistent state (registers).  Everything that is only needed when a step ENDS -- integral
+    // errors, the goal of the step in flight, episode return / length / index -- lives in the lane's stash in
+    // shared memory instead: 168 registers are all a thread gets at 12 warps per SM.
     bool busy = false, fin = false, need_init = false;
     int64_t e = 0;
     int k = 0;
-    T x[3], y[14], W3 = 0, I[8], K0[14];
-    T p_m = 1, p_d = 0, p_J1 = 1, p_J3 = 1, p_ctf = 0, p_ctw = 1;
+    T x[3], y[14], W3 = 0, K0[14];
     Dyn<T> d;
     OdeLane<T> ode;
-    T ep_ret[2] = {0, 0};
-    int ep_len = 0;
-    uint32_t ep_idx = 0;
-    T g_b1d[3] = {1, 0, 0}, g_Wd[3] = {0, 0, 0};   // mode-0 goal of the step in flight (xd = vd = 0): no reload at the end
+    constexpr int S_I = 0, S_B1D = 8, S_WD = 11, S_RET0 = 14, S_LEN = 15, S_IDX = 16, S_RET1 = 17;   // stash slots: env in flight
+    constexpr int S_ACT = 18, S_PAR = 23, S_NB1D = 29;   // next env, fetched ahead: action (<= 5), parameters (6), b1d (3)
+    bool has_next = false;   // K0 / d hold the NEXT env's state (loads in flight), the stash its action etc.
+    int64_t e_next = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = 0;
 #pragma unroll
     for (int i = 0; i < 14; ++i) { y[i] = 0; K0[i] = 0; }
     y[3] = 1; y[7] = 1; y[11] = 1;   // idle lanes run the (warp-uniform) attempt on a benign state: R = I
-#pragma unroll
-    for (int i = 0; i < 8; ++i) I[i] = 0;
     d.fm = d.g = d.Mi0 = d.Mi1 = d.kw0 = d.kw1 = d.w3dot = 0;
     ode.t = 0; ode.h_abs = c.dt; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0; ode.checked = 0;
 
-    // queued resets (single-step launches): lane i resets the env in RQ[i] -- all queued envs at once -- and
-    // writes the new episode's state, integrals and first observation straight to the arrays.  The lanes' own
-    // env registers are not involved: the reset works through shared scratch (the stage storage, free in phase A).
-    int rq_n = 0;                                                          // warp-uniform: entries in RQ
-    const bool defer_ok = a.n_steps == 1 && N < ((int64_t)1 << 31);        // kernel-uniform
-    auto flush_resets = [&]() {
-        __syncwarp();
-        if (lane < rq_n) {
-            const int64_t er = (int64_t)rq[lane];
-            const uint32_t ep = __ldcg(a.ep_index + er);   // written when the env was released (already incremented)
-            auto_reset_env<T, MODE>(&a, er, ep, os + lane * O, ks + lane * 32);
-            const T* sc = ks + lane * 32;
-#pragma unroll
-            for (int i = 0; i < 18; ++i) a.state[i * N + er] = sc[i];   // scratch order = state row order
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a.integ[i * N + er] = sc[18 + i];
-            float* d1 = a.obs_roll ? a.obs_roll + er * O : a.obs + er * O;
-#pragma unroll
-            for (int i = 0; i < O; ++i) d1[i] = os[lane * O + i];
-            if (a.obs_roll) {
-#pragma unroll 1
-                for (int i = 0; i < O; ++i) a.obs[er * O + i] = os[lane * O + i];
-            }
-        }
-        __syncwarp();
-        rq_n = 0;
-    };
+    int rq_n = 0;   // warp-uniform: entries in RQ
 
     for (;;) {
         // =============================== phase A ===============================
-        // ---- A1: finish the env.step that just completed ----
         const unsigned finmask = __ballot_sync(FULL, fin);
+        bool rs_pending = false; int64_t rs_e = 0; uint32_t rs_ep = 0; float *rs_o1 = nullptr, *rs_o2 = nullptr;   // multi-step: this lane's env needs a reset
+        // ---- A0: lanes that are idle, or about to release their env, are given the next env of the warp's sequence
+        // NOW and start fetching it: the state into the (dead) registers of K0 and d, action / parameters / goal
+        // into the stash with cp.async.  The round trip to HBM overlaps the end-of-step work below instead of
+        // stalling the start of the next step.
+        {
+            const bool leaving = fin && (k == a.n_steps - 1);
+            const unsigned need = __ballot_sync(FULL, (!busy || leaving) && !has_next);
+            const int cnt = __popc(need);
+            if (cnt && !(exhausted && tile_pos >= 32)) {
+                const int rank = __popc(need & ((1u << lane) - 1u));
+                const int rem = 32 - tile_pos;
+                int64_t base2 = -1;
+                if (cnt > rem && !exhausted) {
+                    unsigned long long t = 0;
+                    if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
+                    t = __shfl_sync(FULL, t, 0);
+                    if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
+                    else exhausted = true;
+                }
+                int64_t ee = a.env_hi;
+                if ((need >> lane) & 1u) {
+                    if (rank < rem) ee = tile_base + tile_pos + rank;
+                    else if (base2 >= 0) ee = base2 + (rank - rem);
+                }
+                if (cnt > rem) { tile_base = base2; tile_pos = (base2 >= 0) ? cnt - rem : 32; }
+                else tile_pos += cnt;
+                if (ee < a.env_hi) {
+                    has_next = true; e_next = ee;
+                    // K0 and d are dead for a lane that is idle or has finished its step (A1 only reads ode's counters)
+                    d.fm = a.state[0 * N + ee]; d.g = a.state[1 * N + ee]; d.Mi0 = a.state[2 * N + ee];
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) K0[i] = a.state[(3 + i) * N + ee];
+                    d.Mi1 = a.state[17 * N + ee];
+                    if (a.actions) {
+                        if (a.act_f32) {
+                            const float* p = (const float*)a.actions + ee * A;
+#pragma unroll
+                            for (int i = 0; i < A; ++i) cp_async<4>(sh + (S_ACT + i) * 32, p + i);
+                        } else if (sizeof(T) == 8) {
+                            const double* p = (const double*)a.actions + ee * A;
+#pragma unroll
+                            for (int i = 0; i < A; ++i) cp_async<8>(sh + (S_ACT + i) * 32, p + i);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        if (MODE == 0 || (i != 1 && i != 4)) cp_async<sizeof(T)>(sh + (S_PAR + i) * 32, a.params + i * N + ee);
+                    }
+                    if (c.goal_mode == 1) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) cp_async<sizeof(T)>(sh + (S_NB1D + i) * 32, a.goal + (6 + i) * N + ee);
+                    }
+                }
+            }
+            cp_async_commit();
+        }
+        // ---- A1: finish the env.step that just completed ----
         if (finmask) {
             __syncwarp();   // phase B is over for every lane: the stage storage may be reused as reset scratch
-            bool did_reset = false, ep_done = false, deferred = false, term = false, trunc = false;
+            bool ep_done = false, deferred = false, term = false, trunc = false;
             int nf = 0, st = 0, nproj = 0, ep_len_done = 0;
             float rew0f = 0.f;
             T ret_done0 = 0, ret_done1 = 0;
+            T In[8];                    // integral errors after this step
+            T ep_ret0 = 0, ep_ret1 = 0; // episode accumulators after this step
+            int ep_len = 0;
+            uint32_t ep_idx = 0;
+            float *obs1 = nullptr, *obs2 = nullptr;   // where this step's observation row goes
             const bool last = (k == a.n_steps - 1);
             if (fin) {
                 float o[23];
                 st = ode.status; nf = ode.nfev; nproj = ode.nproj;
+                cp_async_wait_group<1>();   // A2's copies into the stash, long done (all but this round's A0 group)
                 EnvRegs<T> r;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) r.x[i] = x[i];
@@ -283,10 +332,14 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 for (int i = 0; i < 14; ++i) r.y[i] = y[i];
                 r.W3 = W3;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) r.I[i] = I[i];
+                for (int i = 0; i < 8; ++i) r.I[i] = sh[(S_I + i) * 32];
+                ep_ret0 = sh[S_RET0 * 32];
+                if (G == 2) ep_ret1 = sh[S_RET1 * 32];
+                ep_len = stash_i32(sh, S_LEN);
+                ep_idx = (uint32_t)stash_i32(sh, S_IDX);
                 if (c.goal_mode == 1) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) { r.goal[i] = 0; r.goal[3 + i] = 0; r.goal[6 + i] = g_b1d[i]; r.goal[9 + i] = g_Wd[i]; }
+                    for (int i = 0; i < 3; ++i) { r.goal[i] = 0; r.goal[3 + i] = 0; r.goal[6 + i] = sh[(S_B1D + i) * 32]; r.goal[9 + i] = sh[(S_WD + i) * 32]; }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * N + e];
@@ -302,16 +355,26 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 } else {
                     int fl = norm_error_state<T>(r, c, o, MODE);
                     if (fl & 2) st |= 4;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) I[i] = r.I[i];
                     reward_done<T>(c, o, rew, dn, MODE);
                 }
-                // the observation row leaves the registers at once (tile row = lane; see the copy below)
 #pragma unroll
-                for (int i = 0; i < O; ++i) os[lane * O + i] = o[i];
+                for (int i = 0; i < 8; ++i) In[i] = r.I[i];
+                // ---- the observation row leaves the registers at once: each lane writes its own row.  Scattered
+                // 4-byte stores, but the rows of neighbouring lanes are adjacent in memory, so L2 assembles full
+                // sectors; measured 5 % faster than a coalescing copy through shared memory (profiles/r01_summary.md)
+                obs1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (last ? a.obs + e * O : nullptr);
+                obs2 = (a.obs_roll && last) ? a.obs + e * O : nullptr;
+                if (obs1) {
+#pragma unroll
+                    for (int i = 0; i < O; ++i) obs1[i] = o[i];
+                }
+                if (obs2) {
+#pragma unroll
+                    for (int i = 0; i < O; ++i) obs2[i] = o[i];
+                }
                 rew0f = (float)rew[0];
-                ep_ret[0] += (T)rew[0];
-                if (G == 2) ep_ret[1] += (T)rew[1];
+                ep_ret0 += (T)rew[0];
+                if (G == 2) ep_ret1 += (T)rew[1];
                 ep_len += 1;
                 term = (dn[0] | dn[1]) != 0;
                 trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
@@ -326,32 +389,26 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (c.diagnostics && last) a.nfev[e] = nf;
                 if (st) a.status[e] |= (uint8_t)st;
                 if (c.autoreset && (term || trunc)) {
-                    ep_len_done = ep_len; ret_done0 = ep_ret[0]; ret_done1 = ep_ret[1];
+                    ep_len_done = ep_len; ret_done0 = ep_ret0; ret_done1 = ep_ret1;
                     if (last) {
 #pragma unroll
                         for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
                     }
                     ep_idx += 1;
-                    ep_ret[0] = 0; ep_ret[1] = 0; ep_len = 0;
+                    ep_ret0 = 0; ep_ret1 = 0; ep_len = 0;
                     ep_done = true;
                 }
             }
-            // ---- auto reset.  A reset is ~1 000 instructions for one lane of the warp; with single-step launches
-            // the env leaves the lane anyway, so its reset is QUEUED (per warp) and a whole batch of queued envs is
-            // reset by all lanes at once further down.  Multi-step launches (the env continues in this lane) and
-            // queue overflow (e.g. a common time limit hitting every env at once) reset on the spot. ----
+            // ---- auto reset: only noted here, carried out further down (see `parked reset`).  Single-step launches
+            // queue the env (it leaves the lane anyway) so that a whole batch is reset at once. ----
             {
                 const unsigned wmask = __ballot_sync(FULL, ep_done);
                 if (wmask) {
-                    if (QR_DEFER_RESET && defer_ok) {
-                        const int pos = rq_n + __popc(wmask & ((1u << lane) - 1u));
-                        if (ep_done && pos < 32) { rq[pos] = (int32_t)e; deferred = true; }
-                        rq_n = min(32, rq_n + __popc(wmask));
-                    }
-                    if (ep_done && !deferred) {
-                        // the new episode's first observation replaces the terminal one in this lane's staging row
-                        auto_reset_env<T, MODE>(&a, e, ep_idx, os + lane * O, ks + lane * 32);   // the stage storage is free in phase A
-                        did_reset = true;
+                    if (!MULTI) {   // RQ holds 64: at most QR_RESET_BATCH - 1 entries from earlier rounds + 32 new ones
+                        if (ep_done) { rq[rq_n + __popc(wmask & ((1u << lane) - 1u))] = (int32_t)e; deferred = true; }
+                        rq_n += __popc(wmask);
+                    } else if (ep_done) {
+                        rs_pending = true; rs_e = e; rs_ep = ep_idx; rs_o1 = obs1; rs_o2 = obs2;
                     }
                 }
             }
@@ -383,41 +440,18 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     }
                 }
             }
-            // ---- observation rows: each finished lane writes its own row from the shared staging row (the new
-            // episode's first observation if the env was just reset).  Scattered 4-byte stores, but the rows of
-            // neighbouring lanes are adjacent in memory, so L2 assembles full sectors; measured 5 % faster than
-            // routing the rows through a coalescing copy loop (profiles/r01_summary.md, r01n).
-            if (fin && !deferred) {
-                const bool lst = (k == a.n_steps - 1);
-                float* d1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (lst ? a.obs + e * O : nullptr);
-                float* d2 = (a.obs_roll && lst) ? a.obs + e * O : nullptr;
-                if (d1) {
-#pragma unroll
-                    for (int i = 0; i < O; ++i) d1[i] = os[lane * O + i];
-                }
-                if (d2) {
-#pragma unroll 1
-                    for (int i = 0; i < O; ++i) d2[i] = os[lane * O + i];
-                }
-            }
-            __syncwarp();
             if (fin) {
                 fin = false;
-                if (did_reset) {
-                    const T* sc = ks + lane * 32;   // what auto_reset_env left in this lane's scratch
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) x[i] = sc[i];
-#pragma unroll
-                    for (int i = 0; i < 14; ++i) y[i] = sc[3 + i];
-                    W3 = sc[17];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) I[i] = sc[18 + i];
-                    p_m = sc[26]; p_J1 = sc[28]; p_J3 = sc[29]; p_ctw = sc[31];
-                    if (MODE == 0) { p_d = sc[27]; p_ctf = sc[30]; }
-                }
                 k += 1;
-                if (k < a.n_steps) need_init = true;
-                else {
+                if (k < a.n_steps) {
+                    need_init = true;   // the env stays in this lane: end-of-step values back into the stash
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sh[(S_I + i) * 32] = In[i];
+                    sh[S_RET0 * 32] = ep_ret0;
+                    if (G == 2) sh[S_RET1 * 32] = ep_ret1;
+                    stash_i32(sh, S_LEN) = ep_len;
+                    stash_i32(sh, S_IDX) = (int32_t)ep_idx;
+                } else {
                     // release the env: state back to HBM (not the terminal state of an env whose reset is queued)
                     if (!deferred) {
 #pragma unroll
@@ -426,71 +460,151 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
                         a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) a.integ[i * N + e] = I[i];
+                        for (int i = 0; i < 8; ++i) a.integ[i * N + e] = In[i];
                     }
-                    a.ep_return[e] = ep_ret[0];
-                    if (G == 2) a.ep_return[N + e] = ep_ret[1];
+                    a.ep_return[e] = ep_ret0;
+                    if (G == 2) a.ep_return[N + e] = ep_ret1;
                     a.ep_length[e] = ep_len;
                     a.ep_index[e] = ep_idx;
                     busy = false;
                 }
             }
-            if (QR_DEFER_RESET && rq_n >= QR_RESET_BATCH) flush_resets();
         }
-        // ---- A2: idle lanes take the next envs of the warp's sequence ----
+        // ---- A2: idle lanes adopt the env fetched in A0 ----
+        if (has_next && !busy) {
+            has_next = false;
+            e = e_next; k = 0; busy = true; need_init = true;
+            x[0] = d.fm; x[1] = d.g; x[2] = d.Mi0; W3 = d.Mi1;
+#pragma unroll
+            for (int i = 0; i < 14; ++i) y[i] = K0[i];
+            // end-of-step values go global -> stash without passing through registers (needed when the step ends)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp_async<sizeof(T)>(sh + (S_I + i) * 32, a.integ + i * N + e);
+            cp_async<sizeof(T)>(sh + S_RET0 * 32, a.ep_return + e);
+            if (G == 2) cp_async<sizeof(T)>(sh + S_RET1 * 32, a.ep_return + N + e);
+            cp_async<4>(&stash_i32(sh, S_LEN), a.ep_length + e);
+            cp_async<4>(&stash_i32(sh, S_IDX), a.ep_index + e);
+        }
+        cp_async_commit();
+        const bool drained = !__any_sync(FULL, busy);
+        // ---- parked reset.  A reset is ~1 000 instructions and out of line; a call from inside this loop would put
+        // every value that lives across it into local memory FOR THE WHOLE LOOP (measured: ~2.5 M local accesses per
+        // launch, in-flight loads serialised behind them).  So the lane state is parked in the stage storage (free in
+        // phase A) around the call and re-defined from there afterwards: nothing is live across it.  Single-step
+        // launches reset a batch of queued envs, one per lane; multi-step launches the lanes' own envs. ----
         {
-            const unsigned need = __ballot_sync(FULL, !busy);
-            const int cnt = __popc(need);
-            if (cnt && !(exhausted && tile_pos >= 32)) {
-                const int rank = __popc(need & ((1u << lane) - 1u));
-                const int rem = 32 - tile_pos;
-                int64_t base2 = -1;
-                if (cnt > rem && !exhausted) {
-                    unsigned long long t = 0;
-                    if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
-                    t = __shfl_sync(FULL, t, 0);
-                    if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
-                    else exhausted = true;
+            bool do_reset = false, r_cont = false;
+            int64_t r_e = 0; uint32_t r_ep = 0; float *r_o1 = nullptr, *r_o2 = nullptr;
+            if (MULTI) {
+                do_reset = rs_pending; r_e = rs_e; r_ep = rs_ep; r_o1 = rs_o1; r_o2 = rs_o2;
+                r_cont = rs_pending && busy && e == rs_e;   // the env continues in this lane
+            } else if (rq_n >= QR_RESET_BATCH || (drained && rq_n > 0)) {
+                // at most 32 per pass; a burst (e.g. a common time limit) leaves the rest for the next round
+                const int n_now = min(rq_n, 32);
+                if (lane < n_now) {
+                    do_reset = true; r_e = (int64_t)rq[rq_n - n_now + lane];
+                    r_ep = __ldcg(a.ep_index + r_e);   // written when the env was released (already incremented)
+                    r_o1 = a.obs_roll ? a.obs_roll + r_e * O : a.obs + r_e * O;
+                    r_o2 = a.obs_roll ? a.obs + r_e * O : nullptr;
                 }
-                int64_t ee = a.env_hi;
-                if (!busy) {
-                    if (rank < rem) ee = tile_base + tile_pos + rank;
-                    else if (base2 >= 0) ee = base2 + (rank - rem);
+                rq_n -= n_now;
+            }
+            if (__any_sync(FULL, do_reset)) {
+                __syncwarp();
+                T* const pk = ks + 1024 + lane;   // park slot j of this lane: pk[j * 32] (the reset scratch is ks[0 .. 1023])
+#define QR_PKI(j) (*reinterpret_cast<int32_t*>(pk + (j) * 32))
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pk[i * 32] = x[i];
+#pragma unroll
+                for (int i = 0; i < 14; ++i) { pk[(3 + i) * 32] = y[i]; pk[(18 + i) * 32] = K0[i]; }
+                pk[17 * 32] = W3;
+                pk[32 * 32] = d.fm; pk[33 * 32] = d.g; pk[34 * 32] = d.Mi0; pk[35 * 32] = d.Mi1; pk[36 * 32] = d.kw0; pk[37 * 32] = d.kw1; pk[38 * 32] = d.w3dot;
+                pk[39 * 32] = ode.t; pk[40 * 32] = ode.h_abs;
+                QR_PKI(41) = ode.rejected; QR_PKI(42) = ode.nfev; QR_PKI(43) = ode.status; QR_PKI(44) = ode.nproj; QR_PKI(45) = ode.checked;
+                QR_PKI(46) = k;
+                QR_PKI(47) = (int)busy | ((int)fin << 1) | ((int)need_init << 2) | ((int)has_next << 3) | ((int)exhausted << 4);
+                QR_PKI(48) = (int32_t)(uint32_t)e; QR_PKI(49) = (int32_t)(e >> 32);
+                QR_PKI(50) = (int32_t)(uint32_t)e_next; QR_PKI(51) = (int32_t)(e_next >> 32);
+                QR_PKI(52) = (int32_t)(uint32_t)tile_base; QR_PKI(53) = (int32_t)(tile_base >> 32);
+                QR_PKI(54) = tile_pos; QR_PKI(55) = rq_n;
+                if (do_reset) {
+                    float dummy[23];
+                    // the new episode's first observation replaces the terminal one in the step's output row
+                    auto_reset_env<T, MODE>(&a, r_e, r_ep, r_o1 ? r_o1 : dummy, r_o2, ks + lane * 32);
                 }
-                if (cnt > rem) { tile_base = base2; tile_pos = (base2 >= 0) ? cnt - rem : 32; }
-                else tile_pos += cnt;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) x[i] = pk[i * 32];
+#pragma unroll
+                for (int i = 0; i < 14; ++i) { y[i] = pk[(3 + i) * 32]; K0[i] = pk[(18 + i) * 32]; }
+                W3 = pk[17 * 32];
+                d.fm = pk[32 * 32]; d.g = pk[33 * 32]; d.Mi0 = pk[34 * 32]; d.Mi1 = pk[35 * 32]; d.kw0 = pk[36 * 32]; d.kw1 = pk[37 * 32]; d.w3dot = pk[38 * 32];
+                ode.t = pk[39 * 32]; ode.h_abs = pk[40 * 32];
+                ode.rejected = QR_PKI(41); ode.nfev = QR_PKI(42); ode.status = QR_PKI(43); ode.nproj = QR_PKI(44); ode.checked = QR_PKI(45);
+                k = QR_PKI(46);
                 {
-                    if (ee < a.env_hi) {
-                        e = ee; k = 0; busy = true; need_init = true;
+                    const int fl = QR_PKI(47);
+                    busy = fl & 1; fin = (fl >> 1) & 1; need_init = (fl >> 2) & 1; has_next = (fl >> 3) & 1; exhausted = (fl >> 4) & 1;
+                }
+                e = (int64_t)(((uint64_t)(uint32_t)QR_PKI(49) << 32) | (uint32_t)QR_PKI(48));
+                e_next = (int64_t)(((uint64_t)(uint32_t)QR_PKI(51) << 32) | (uint32_t)QR_PKI(50));
+                tile_base = (int64_t)(((uint64_t)(uint32_t)QR_PKI(53) << 32) | (uint32_t)QR_PKI(52));
+                tile_pos = QR_PKI(54); rq_n = QR_PKI(55);
+#undef QR_PKI
+                if (do_reset) {
+                    const T* sc = ks + lane * 32;   // what auto_reset_env left in this lane's scratch
+                    if (r_cont) {
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) x[i] = a.state[i * N + e];
+                        for (int i = 0; i < 3; ++i) x[i] = sc[i];
 #pragma unroll
-                        for (int i = 0; i < 12; ++i) y[i] = a.state[(3 + i) * N + e];
-                        y[12] = a.state[15 * N + e]; y[13] = a.state[16 * N + e]; W3 = a.state[17 * N + e];
+                        for (int i = 0; i < 14; ++i) y[i] = sc[3 + i];
+                        W3 = sc[17];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) I[i] = a.integ[i * N + e];
-                        p_m = a.params[0 * N + e]; p_J1 = a.params[2 * N + e]; p_J3 = a.params[3 * N + e]; p_ctw = a.params[5 * N + e];
-                        if (MODE == 0) { p_d = a.params[1 * N + e]; p_ctf = a.params[4 * N + e]; }
-                        ep_ret[0] = a.ep_return[e];
-                        ep_ret[1] = (G == 2) ? a.ep_return[N + e] : (T)0;
-                        ep_len = a.ep_length[e];
-                        ep_idx = a.ep_index[e];
+                        for (int i = 0; i < 8; ++i) sh[(S_I + i) * 32] = sc[18 + i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 18; ++i) a.state[i * N + r_e] = sc[i];   // scratch order = state row order
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a.integ[i * N + r_e] = sc[18 + i];
                     }
                 }
+                __syncwarp();
             }
         }
-        if (!__any_sync(FULL, busy)) {
-            if (QR_DEFER_RESET && rq_n) flush_resets();
-            break;
-        }
+        if (drained && (MULTI || rq_n == 0)) break;
         // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
         if (busy && need_init) {
             need_init = false;
+#pragma unroll
+            for (int i = 0; i < 14; ++i) K0[i] = 0;   // dead here on every path (liveness hint, as in A1)
             // every load of this phase is issued before the first consumer (in-order issue: a stalled
             // consumer would otherwise delay the independent loads behind it by a full memory round trip)
             T act[5], b1d[3];
+            T p_m, p_J1, p_J3, p_ctw, p_d = 0, p_ctf = 0;
             bool act_f32 = a.act_f32 != 0;
-            if (a.actions) {
+            const bool staged_act = a.actions && (a.act_f32 || sizeof(T) == 8);   // what A0 can stage (kernel-uniform)
+            if (k == 0) {
+                // first step of an env adopted in A2: action, parameters and b1d were fetched ahead into the stash
+                cp_async_wait_group<1>();   // everything but A2's group (end-of-step values, not needed yet)
+                p_m = sh[(S_PAR + 0) * 32]; p_J1 = sh[(S_PAR + 2) * 32]; p_J3 = sh[(S_PAR + 3) * 32]; p_ctw = sh[(S_PAR + 5) * 32];
+                if (MODE == 0) { p_d = sh[(S_PAR + 1) * 32]; p_ctf = sh[(S_PAR + 4) * 32]; }
+                if (staged_act) {
+#pragma unroll
+                    for (int i = 0; i < A; ++i)
+                        act[i] = a.act_f32 ? (T)*reinterpret_cast<const float*>(sh + (S_ACT + i) * 32) : sh[(S_ACT + i) * 32];
+                }
+                if (c.goal_mode == 1) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) b1d[i] = sh[(S_NB1D + i) * 32];
+                }
+            } else {
+                p_m = a.params[0 * N + e]; p_J1 = a.params[2 * N + e]; p_J3 = a.params[3 * N + e]; p_ctw = a.params[5 * N + e];
+                if (MODE == 0) { p_d = a.params[1 * N + e]; p_ctf = a.params[4 * N + e]; }
+                if (c.goal_mode == 1) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
+                }
+            }
+            if (a.actions && !(k == 0 && staged_act)) {
                 const int64_t base = ((int64_t)k * N + e) * A;
                 if (a.act_f32) {
                     const float* p = (const float*)a.actions + base;
@@ -507,10 +621,6 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                 }
             }
-            if (c.goal_mode == 1) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
-            }
             if (c.goal_mode != 1) {   // the observation at the end of this step reads the goal: have it in L2 by then
 #pragma unroll
                 for (int i = 0; i < 12; ++i) prefetch_l2(a.goal + i * N + e);
@@ -518,6 +628,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             if (!a.actions) {
                 const uint64_t gid = (uint64_t)(a.env_id_offset + e);
                 uint32_t rnd[8];
+                cp_async_wait_all();
+                const uint32_t ep_idx = (uint32_t)stash_i32(sh, S_IDX);
+                const int ep_len = stash_i32(sh, S_LEN);
                 ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len, rnd);
                 if (A == 5) ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len + 1u, rnd + 4);
 #pragma unroll
@@ -539,7 +652,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 T Wd[3];
                 traj_wd<T>(y + 3, Wv, b1d, Wd);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) { g_b1d[i] = b1d[i]; g_Wd[i] = Wd[i]; }
+                for (int i = 0; i < 3; ++i) { sh[(S_B1D + i) * 32] = b1d[i]; sh[(S_WD + i) * 32] = Wd[i]; }   // for the observation at the end
                 if (k == a.n_steps - 1) {   // visible in the goal buffer like env.Wd after set_goal_state
 #pragma unroll
                     for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];

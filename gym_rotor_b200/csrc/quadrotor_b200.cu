@@ -51,7 +51,7 @@ struct qr_handle {
     double* d_stage; size_t d_stage_bytes;
     cudaStream_t io_stream;
     unsigned long long* tile_counter;
-    int num_sms; int smem_optin; int attr_set[2];
+    int num_sms; int smem_optin; int attr_set[4];
 };
 
 namespace {
@@ -108,11 +108,16 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     if (grid > h->num_sms) grid = h->num_sms;
     if (ntiles < (int64_t)warps) warps = (int)ntiles;
     const size_t smem = per_warp * warps;
-    void (*kern)(const qr::StepArgs<T>) = (h->cfg.mode == QR_MODE_COUPLED) ? qr::k_step<T, 1>
-                                          : (h->cfg.mode == QR_MODE_DECOUPLED) ? qr::k_step<T, 2> : qr::k_step<T, 0>;
-    if (!h->attr_set[sizeof(T) == 8]) {
+    // single-step launches queue the envs whose episode ended and reset them in a second kernel; multi-step
+    // launches (the env keeps stepping in its lane) reset inside the step kernel
+    const bool multi = n_steps > 1;
+    void (*kern)(const qr::StepArgs<T>);
+    if (multi) kern = (h->cfg.mode == QR_MODE_COUPLED) ? qr::k_step<T, 1, true> : (h->cfg.mode == QR_MODE_DECOUPLED) ? qr::k_step<T, 2, true> : qr::k_step<T, 0, true>;
+    else kern = (h->cfg.mode == QR_MODE_COUPLED) ? qr::k_step<T, 1, false> : (h->cfg.mode == QR_MODE_DECOUPLED) ? qr::k_step<T, 2, false> : qr::k_step<T, 0, false>;
+    const int attr_idx = (sizeof(T) == 8 ? 2 : 0) + (multi ? 1 : 0);
+    if (!h->attr_set[attr_idx]) {
         QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->smem_optin / per_warp * per_warp)));
-        h->attr_set[sizeof(T) == 8] = 1;
+        h->attr_set[attr_idx] = 1;
     }
     kern<<<(unsigned)grid, warps * 32, smem, s>>>(a);
     g_launches++;
@@ -162,6 +167,7 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     if (c->n_envs <= 0) return fail(QR_ERR_INVALID, "qr_create: n_envs must be positive");
     if (c->mode < 0 || c->mode > 2) return fail(QR_ERR_INVALID, "qr_create: bad mode");
     if (c->dtype != QR_F32 && c->dtype != QR_F64) return fail(QR_ERR_INVALID, "qr_create: bad dtype");
+    if (c->n_envs >= ((int64_t)1 << 31)) return fail(QR_ERR_INVALID, "qr_create: n_envs must be below 2^31 per handle");
     if (c->integrator == QR_INT_EULER && c->mode != QR_MODE_QUAD)
         return fail(QR_ERR_INVALID, "qr_create: the Euler integrator exists only for the base Quad-v0 env (quad.py:252)");
     if (c->goal_mode < QR_GOAL_EXTERNAL || c->goal_mode > QR_GOAL_TRAJ_EIGHT) return fail(QR_ERR_INVALID, "qr_create: bad goal_mode");

@@ -168,7 +168,7 @@ class BatchedQuadEnv:
             self.goal_update()      # trajectory_generator.get_desired on the pre-step state, main.py:145-147
         nat.check(self._L.qr_step(self._h, C.c_void_p(action.data_ptr()),
                                   nat.F64 if action.dtype == torch.float64 else nat.F32, self._stream()))
-        return self._split_obs(self.obs), self.reward, self.done.bool(), False, {}
+        return self._split_obs(self.obs), self.reward, self.done.view(torch.bool), False, {}   # flags are 0/1 bytes: reinterpreted, not copied
 
     def policy_td3(self, out=None):
         """Actions of the reference's shipped TD3 actor(s) for the current observations, computed on device
