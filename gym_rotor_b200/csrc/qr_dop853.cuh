@@ -28,6 +28,9 @@
 #include "qr_math.cuh"
 #include "dop853_tableau.h"
 
+#ifndef QR_PIPE
+#define QR_PIPE 1
+#endif
 namespace qr {
 
 // ---- tableau in constant memory (uniform-indexed loads in the rolled stage loop) ------------------------
@@ -341,15 +344,42 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         // couplings A[s][j], j >= 1, from the flattened table (constant bank, uniform datapath)
         // (measured and dropped: two K vectors per trip / software pipelining -- the extra registers cost more
         //  than the exposed LDS latency, profiles/r01_summary.md)
-        const int p1 = TB::Ps(s + 1);
+#if QR_PIPE
+        // two K vectors in flight: the loads of the next one are issued before the sums of the current one
+        if (sizeof(T) == 4) {
+            int p = TB::Ps(s);
+            int n = TB::Ps(s + 1) - p;
+            if (n > 0) {
+                T ka[14], kb[14];
+                TabEntry<T> te = TB::P(p);
+                T ca = h * te.c, cb;
+                ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, ka);
 #pragma unroll 1
-        for (int p = TB::Ps(s); p < p1; ++p) {
-            const TabEntry<T> te = TB::P(p);
-            const T c = h * te.c;
-            T k[14];
-            if (sizeof(T) == 4) ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, k);
-            else ks_load_lane<T>(reinterpret_cast<const T*>(reinterpret_cast<const char*>(kl) + te.off), lane, k);
-            axpy14<T>(c, k, ys);
+                for (;;) {
+                    if (n == 1) { axpy14<T>(ca, ka, ys); break; }
+                    te = TB::P(p + 1); cb = h * te.c;
+                    ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, kb);
+                    axpy14<T>(ca, ka, ys);
+                    if (n == 2) { axpy14<T>(cb, kb, ys); break; }
+                    te = TB::P(p + 2); ca = h * te.c;
+                    ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, ka);
+                    axpy14<T>(cb, kb, ys);
+                    p += 2; n -= 2;
+                }
+            }
+        } else
+#endif
+        {
+            const int p1 = TB::Ps(s + 1);
+#pragma unroll 1
+            for (int p = TB::Ps(s); p < p1; ++p) {
+                const TabEntry<T> te = TB::P(p);
+                const T c = h * te.c;
+                T k[14];
+                if (sizeof(T) == 4) ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, k);
+                else ks_load_lane<T>(reinterpret_cast<const T*>(reinterpret_cast<const char*>(kl) + te.off), lane, k);
+                axpy14<T>(c, k, ys);
+            }
         }
         const T W3s = N::fma(h * TB::C(s), d.w3dot, W3);
         {

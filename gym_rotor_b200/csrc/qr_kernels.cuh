@@ -195,7 +195,10 @@ template <typename T> struct warp_smem {
     static constexpr size_t bytes = ks_bytes + os_bytes + ws_bytes + rq_bytes;   // multiple of 16
 };
 
-template <typename T, int MODE, bool MULTI>
+// GOAL1: the goal is generated on the device in trajectory mode 0 (config goal_mode == 1) -- a template parameter so
+// that this configuration has no global load at the end of a step (it would share a scoreboard with the loads that
+// fetch the next env, and wait for them).
+template <typename T, int MODE, bool MULTI, bool GOAL1>
 __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid_constant__ StepArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < 6; ++i) {
                         if (MODE == 0 || (i != 1 && i != 4)) cp_async<sizeof(T)>(sh + (S_PAR + i) * 32, a.params + i * N + ee);
                     }
-                    if (c.goal_mode == 1) {
+                    if (GOAL1) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i) cp_async<sizeof(T)>(sh + (S_NB1D + i) * 32, a.goal + (6 + i) * N + ee);
                     }
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (G == 2) ep_ret1 = sh[S_RET1 * 32];
                 ep_len = stash_i32(sh, S_LEN);
                 ep_idx = (uint32_t)stash_i32(sh, S_IDX);
-                if (c.goal_mode == 1) {
+                if (GOAL1) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) { r.goal[i] = 0; r.goal[3 + i] = 0; r.goal[6 + i] = sh[(S_B1D + i) * 32]; r.goal[9 + i] = sh[(S_WD + i) * 32]; }
                 } else {
@@ -592,14 +595,14 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < A; ++i)
                         act[i] = a.act_f32 ? (T)*reinterpret_cast<const float*>(sh + (S_ACT + i) * 32) : sh[(S_ACT + i) * 32];
                 }
-                if (c.goal_mode == 1) {
+                if (GOAL1) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) b1d[i] = sh[(S_NB1D + i) * 32];
                 }
             } else {
                 p_m = a.params[0 * N + e]; p_J1 = a.params[2 * N + e]; p_J3 = a.params[3 * N + e]; p_ctw = a.params[5 * N + e];
                 if (MODE == 0) { p_d = a.params[1 * N + e]; p_ctf = a.params[4 * N + e]; }
-                if (c.goal_mode == 1) {
+                if (GOAL1) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
                 }
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                 }
             }
-            if (c.goal_mode != 1) {   // the observation at the end of this step reads the goal: have it in L2 by then
+            if (!GOAL1) {   // the observation at the end of this step reads the goal: have it in L2 by then
 #pragma unroll
                 for (int i = 0; i < 12; ++i) prefetch_l2(a.goal + i * N + e);
             }
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             for (int i = 0; i < 14; ++i) r.y[i] = y[i];
             r.W3 = W3;
             r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
-            if (c.goal_mode == 1) {   // goal from the pre-step state, main.py:145-147
+            if (GOAL1) {   // goal from the pre-step state, main.py:145-147
                 const T Wv[3] = {y[12], y[13], W3};
                 T Wd[3];
                 traj_wd<T>(y + 3, Wv, b1d, Wd);

@@ -51,7 +51,7 @@ struct qr_handle {
     double* d_stage; size_t d_stage_bytes;
     cudaStream_t io_stream;
     unsigned long long* tile_counter;
-    int num_sms; int smem_optin; int attr_set[4];
+    int num_sms; int smem_optin; int attr_set[8];
 };
 
 namespace {
@@ -111,10 +111,17 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     // single-step launches queue the envs whose episode ended and reset them in a second kernel; multi-step
     // launches (the env keeps stepping in its lane) reset inside the step kernel
     const bool multi = n_steps > 1;
+    const bool goal1 = h->cfg.goal_mode == QR_GOAL_TRAJ_MODE0;   // only with a wrapper mode (checked in qr_create)
     void (*kern)(const qr::StepArgs<T>);
-    if (multi) kern = (h->cfg.mode == QR_MODE_COUPLED) ? qr::k_step<T, 1, true> : (h->cfg.mode == QR_MODE_DECOUPLED) ? qr::k_step<T, 2, true> : qr::k_step<T, 0, true>;
-    else kern = (h->cfg.mode == QR_MODE_COUPLED) ? qr::k_step<T, 1, false> : (h->cfg.mode == QR_MODE_DECOUPLED) ? qr::k_step<T, 2, false> : qr::k_step<T, 0, false>;
-    const int attr_idx = (sizeof(T) == 8 ? 2 : 0) + (multi ? 1 : 0);
+    if (h->cfg.mode == QR_MODE_COUPLED)
+        kern = multi ? (goal1 ? qr::k_step<T, 1, true, true> : qr::k_step<T, 1, true, false>)
+                     : (goal1 ? qr::k_step<T, 1, false, true> : qr::k_step<T, 1, false, false>);
+    else if (h->cfg.mode == QR_MODE_DECOUPLED)
+        kern = multi ? (goal1 ? qr::k_step<T, 2, true, true> : qr::k_step<T, 2, true, false>)
+                     : (goal1 ? qr::k_step<T, 2, false, true> : qr::k_step<T, 2, false, false>);
+    else
+        kern = multi ? qr::k_step<T, 0, true, false> : qr::k_step<T, 0, false, false>;
+    const int attr_idx = (sizeof(T) == 8 ? 4 : 0) + (multi ? 2 : 0) + (goal1 ? 1 : 0);
     if (!h->attr_set[attr_idx]) {
         QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->smem_optin / per_warp * per_warp)));
         h->attr_set[attr_idx] = 1;
