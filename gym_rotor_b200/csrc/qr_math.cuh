@@ -157,13 +157,17 @@ template <typename T> __device__ __noinline__ int project_so3(T* R)
 // convergence is quadratic, so an orthogonality defect of 1e-2 needs three steps to reach float64 rounding.
 // This is the common case (the Euler probe of select_initial_step leaves SO(3) by (h0 |W|)^2 ~ 1e-4..1e-2 in
 // ~12 % of env-steps); it stays in registers.  Returns false if the input is not in that regime.
-template <typename T> QR_DEV bool polar_newton(T* R)
+// float32: the number of steps is fixed a priori from the defect d = max |X^T X - I| measured by so3_ok (singular
+// values within 1.5 d of 1; one step maps an error e to e^2/2): 1 step for d <= 2e-4, 2 for d <= 1.5e-2, else 3
+// reach float32 rounding -- no extra step just to observe convergence (all lanes of a warp pay for the slowest).
+template <typename T> QR_DEV bool polar_newton(T* R, T defect)
 {
     using N = num<T>;
     T X[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) X[i] = R[i];
-    const int iters = (sizeof(T) == 8) ? 5 : 3;
+    const bool apriori = sizeof(T) == 4;
+    const int iters = (sizeof(T) == 8) ? 5 : (defect <= (T)2e-4 ? 1 : (defect <= (T)1.5e-2 ? 2 : 3));
     T delta = 0;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
@@ -180,12 +184,12 @@ template <typename T> QR_DEV bool polar_newton(T* R)
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             const T xn = N::fma(C[i], hid, (T)0.5 * X[i]);
-            delta = N::max(delta, N::abs(xn - X[i]));
+            if (!apriori) delta = N::max(delta, N::abs(xn - X[i]));
             X[i] = xn;
         }
-        if (delta <= ((sizeof(T) == 8) ? (T)1e-15 : (T)2e-7)) break;
+        if (!apriori && delta <= (T)1e-15) break;
     }
-    if (!(delta <= ((sizeof(T) == 8) ? (T)1e-12 : (T)1e-5))) return false;
+    if (!apriori && !(delta <= (T)1e-12)) return false;
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = X[i];
     return true;
@@ -198,7 +202,7 @@ template <typename T, bool NEWTON = false> QR_DEV int ensure_so3(T* R)
 {
     T defect;
     if (so3_ok(R, &defect)) return 0;
-    if (NEWTON) { if (defect < (T)0.05 && polar_newton<T>(R)) return 1; }
+    if (NEWTON) { if (defect < (T)0.05 && polar_newton<T>(R, defect)) return 1; }
     T tmp[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) tmp[i] = R[i];
