@@ -324,6 +324,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             uint32_t ep_idx = 0;
             float *obs1 = nullptr, *obs2 = nullptr;   // where this step's observation row goes
             const bool last = (k == a.n_steps - 1);
+            // all 32 lanes finish the same sub-step of 32 consecutive envs, first one 4-aligned (16-byte aligned rows block)
+            const int64_t e_first = __shfl_sync(FULL, e, 0);
+            const int k_first = __shfl_sync(FULL, k, 0);
+            const bool same = __all_sync(FULL, e - lane == e_first && k == k_first);   // (no warp primitive behind a short-circuit)
+            const bool coop = finmask == FULL && same && (e_first & 3) == 0 &&
+                              (!a.obs_roll || ((reinterpret_cast<uintptr_t>(a.obs_roll) + (size_t)(((int64_t)k * N + e_first) * O) * 4) & 15) == 0);
             if (fin) {
                 float o[23];
                 st = ode.status; nf = ode.nfev; nproj = ode.nproj;
@@ -362,18 +368,26 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) In[i] = r.I[i];
-                // ---- the observation row leaves the registers at once: each lane writes its own row.  Scattered
-                // 4-byte stores, but the rows of neighbouring lanes are adjacent in memory, so L2 assembles full
-                // sectors; measured 5 % faster than a coalescing copy through shared memory (profiles/r01_summary.md)
+                // ---- the observation row leaves the registers at once.  General case: each lane writes its own row
+                // (scattered 4-byte stores; the rows of neighbouring lanes are adjacent in memory, so L2 assembles
+                // full sectors; measured 5 % faster than a general coalescing copy through shared memory).  When the
+                // whole warp finishes 32 consecutive envs together (`coop`: the lock-step regime of a trained
+                // policy), the rows go through a shared tile and leave as 16-byte stores of one contiguous block.
                 obs1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (last ? a.obs + e * O : nullptr);
                 obs2 = (a.obs_roll && last) ? a.obs + e * O : nullptr;
-                if (obs1) {
+                if (coop) {
+                    float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
 #pragma unroll
-                    for (int i = 0; i < O; ++i) obs1[i] = o[i];
-                }
-                if (obs2) {
+                    for (int i = 0; i < O; ++i) tile[lane * O + i] = o[i];
+                } else {
+                    if (obs1) {
 #pragma unroll
-                    for (int i = 0; i < O; ++i) obs2[i] = o[i];
+                        for (int i = 0; i < O; ++i) obs1[i] = o[i];
+                    }
+                    if (obs2) {
+#pragma unroll
+                        for (int i = 0; i < O; ++i) obs2[i] = o[i];
+                    }
                 }
                 rew0f = (float)rew[0];
                 ep_ret0 += (T)rew[0];
@@ -401,6 +415,23 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     ep_ret0 = 0; ep_ret1 = 0; ep_len = 0;
                     ep_done = true;
                 }
+            }
+            if (coop) {
+                __syncwarp();
+                const float4* tile4 = reinterpret_cast<const float4*>(ks);
+                constexpr int NV = 32 * O / 4;   // float4 elements of the 32-row block
+                float4* g1 = reinterpret_cast<float4*>(a.obs_roll ? a.obs_roll + ((int64_t)k * N + e_first) * O : (last ? a.obs + e_first * O : nullptr));
+                float4* g2 = reinterpret_cast<float4*>((a.obs_roll && last) ? a.obs + e_first * O : nullptr);
+#pragma unroll
+                for (int it = 0; it < (NV + 31) / 32; ++it) {
+                    const int q = it * 32 + lane;
+                    if (q < NV) {
+                        const float4 v = tile4[q];
+                        if (g1) g1[q] = v;
+                        if (g2) g2[q] = v;
+                    }
+                }
+                __syncwarp();
             }
             // ---- auto reset: only noted here, carried out further down (see `parked reset`).  Single-step launches
             // queue the env (it leaves the lane anyway) so that a whole batch is reset at once. ----
