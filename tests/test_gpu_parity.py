@@ -190,6 +190,32 @@ def test_fused_rollout_equals_single_steps(dtype):
     e1.close(); e2.close()
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fused_rollout_with_autoreset_equals_single_steps(dtype):
+    """Multi-step launches reset an env inside the kernel (the env keeps stepping in its lane), single-step launches
+    queue the env and reset a batch at a time: same episodes, observations and states.  A 7-step time limit makes
+    every env truncate at once (a burst larger than the queue batch); n is odd, so the rows of the rollout storage
+    are not 16-byte aligned (the coalesced observation path must fall back to per-lane stores)."""
+    n, K = 1001, 20
+    rng = np.random.default_rng(15)
+    acts = _t(rng.uniform(-1, 1, (K, n, 4)), dtype)
+    kw = dict(seed=5, autoreset=True, goal_mode="traj0", max_episode_steps=7)
+    e1 = _env(n, "MONO", dtype, **kw); e2 = _env(n, "MONO", dtype, **kw)
+    for e in (e1, e2):
+        e.reset(); e.init_goal(); e.get_norm_error_state()
+    obs_r, rew_r, done_r = e1.rollout(K, acts, store=True)
+    for k in range(K):
+        obs, rew, done, _, _ = e2.step(acts[k])
+        assert torch.equal(obs[0], obs_r[k]), k
+        assert torch.equal(rew, rew_r[k]) and torch.equal(done, done_r[k].bool())
+    assert torch.equal(e1.state_soa, e2.state_soa) and torch.equal(e1.integ_soa, e2.integ_soa)
+    assert torch.equal(e1.params_soa, e2.params_soa) and torch.equal(e1.goal_soa, e2.goal_soa)
+    assert torch.equal(e1.obs, e2.obs)
+    s1, s2 = e1.stats(), e2.stats()
+    assert s1[0] == s2[0] and s1[0] >= 2 * n and s1[7] == K * n      # episodes ended, env-steps
+    e1.close(); e2.close()
+
+
 def _philox_uniforms(seed, gids, episode):
     u = np.empty((len(gids), 20))
     for i, gid in enumerate(gids):
