@@ -28,7 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 ALG_BYTES = {"MONO_f32": 366, "MONO_f64": 614, "MODUL_f32": 363}   # SURVEY 8(d), per env-step
 ALG_FLOPS = 5450                                                   # SURVEY 8(d), one DOP853 attempt
 STATS_EVERY = 128
-DRAM_BYTES_PER_ENV_STEP_NCU = 388.6   # ncu --set full capture r01m: 814.9 MB per launch of 2^21 env-steps
+DRAM_BYTES_PER_ENV_STEP_NCU = 428.5   # ncu --set full capture r01u (steady state, ~32 k resets in the launch): 898.6 MB per launch of 2^21 env-steps
 
 
 def _peaks():
@@ -285,7 +285,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": (DRAM_BYTES_PER_ENV_STEP_NCU * n * fused / 1e9) if (fw == "MONO" and args.dtype == "f32") else None,
-                         "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01m_kstep_f32_ncu_digest.txt)",
+                         "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01u_kstep_f32_ncu_digest.txt)",
                          "peak_source": which, "kernel": "qr::k_step<%s>" % ("double" if args.dtype == "f64" else "float"),
                          "algorithmic_bytes_per_env_step": bytes_per, "kernel_ms": kernel_ms},
             "roofline_fp": {"bound": "fp%s issue" % ("64" if args.dtype == "f64" else "32"),
