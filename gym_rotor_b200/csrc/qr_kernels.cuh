@@ -1,10 +1,10 @@
 // qr_kernels.cuh -- the fused env.step() kernel and its small companions (reset, goal init, observation).
 //
 // Step kernel: persistent warps, one env per lane, structure-of-arrays state ([component][env], coalesced),
-// state resident in registers across `n_steps` fused sub-steps, DOP853 stage derivatives in shared memory,
-// float32 observations staged through a per-warp shared tile so that the row-major [N][O] output leaves as
-// full 128-byte lines.  No tensor cores: the dynamics are not a dense contraction; the roofline that binds is
-// FP32/FP64 instruction issue.
+// state resident in registers across `n_steps` fused sub-steps, DOP853 stage derivatives and the values that
+// are only needed at the end of a step in shared memory, the next env fetched ahead of the end-of-step work.
+// No tensor cores: the dynamics are not a dense contraction; the roofline that binds is FP32/FP64 instruction
+// issue.
 //
 // Replaces QuadEnv.step (gym_rotor/envs/quad.py:142-168) with its wrappers' overrides
 // (coupled_yaw_wrapper.py:44-110, decoupled_yaw_wrapper.py:49-161) and the trainer's reset protocol
@@ -177,16 +177,18 @@ QR_DEV float warp_sum_f(float v)
 // controller costs the extra attempts it needs (about 6 % under random actions) instead of doubling the
 // work of the whole warp.
 //
-// Warp w of the grid owns the 32-env tiles w, w + W, w + 2W, ... (W = warps in the grid); lanes take
-// consecutive envs from that sequence, so loads and stores of a refill are coalesced.  Observations go
-// through a per-warp shared tile and leave as full 128-byte lines.  Episode statistics are reduced with
-// warp votes / REDUX into per-warp shared accumulators (no per-lane counters: registers are the scarce
-// resource at 12 warps per SM) and flushed with one atomic per statistic and warp at the end.
+// Warps draw 32-env tiles from a per-launch atomic counter; lanes take consecutive envs of the warp's tile
+// sequence, so the loads and stores of a refill are coalesced.  A lane writes its observation row itself, or
+// -- when the whole warp finishes 32 consecutive envs together -- the rows leave as one contiguous block
+// through a shared tile.  Episode statistics are reduced with warp votes / REDUX into per-warp shared
+// accumulators (no per-lane counters: registers are the scarce resource at 12 warps per SM) and flushed with
+// one atomic per statistic and warp at the end.  Phase A in order: A0 fetch the next env ahead, A1 finish the
+// step, (parked) auto reset, A2 adopt the fetched env, A3 start the next step.
 //
 // Per-warp shared memory: KS[8][14][32] T (stage derivatives) | STASH[36][32] T (per-lane values that are only needed
 //                         when a step ends: integrals, goal, episode counters; and the landing zone of the next
 //                         env's action / parameters / goal, fetched ahead) | WS[16] f64 (statistics) |
-//                         RQ[32] i32 (envs whose reset is pending, see below)
+//                         RQ[64] i32 (single-step launches: envs whose reset is queued, see `parked reset`)
 template <typename T> struct warp_smem {
     static constexpr size_t ks_bytes = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T);
     static constexpr size_t os_bytes = 32 * 36 * sizeof(T);   // the stash: 36 slots per lane
