@@ -1,8 +1,9 @@
-// qr_traj.cuh -- on-device goal generation for trajectory modes 1 (hover), 5 (circle), >= 6 (figure eight) and the
-// manual-mode fallback after a trajectory completes.
+// qr_traj.cuh -- on-device goal generation for trajectory modes 1 (hover), 2 (take-off), 3 (land), 4 (stay),
+// 5 (circle), >= 6 (figure eight) and the manual-mode fallback after a trajectory completes.
 //
 // Restates utils/trajectory_generator.py:113-173 (get_desired / calculate_desired / Wd), 176-229 (mark_traj_start,
-// clock), 232-277 (manual, hovering), 359-412 (circle), 415-505 (eight_shaped_curve).  Mode 0 lives in qr_env.cuh
+// clock), 232-277 (manual, hovering), 280-357 (takeoff, waypoint_reached, land, stay), 359-412 (circle), 415-505
+// (eight_shaped_curve).  Mode 0 lives in qr_env.cuh
 // (it is evaluated inside the step kernel).  Per-env trajectory state ts[12]:
 //   0 t | 1 flags (bit0 trajectory_started, bit1 manual_mode, bit2 manual_mode_init) | 2..4 x_init / centre |
 //   5 theta_init | 6 w_b1d | 7 smooth_term | 8 t_traj | 9,10 b1d_dot x,y | 11 unused
@@ -66,15 +67,48 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
             ts[8] = (T)2 + ((T)5 - (T)2) * u_ttraj;
             ts[7] = (T)6.907755278982137 / ts[8];                       // -log(0.001) / t_traj
             ts[6] = (T)-0.15 * PI + ((T)0.15 * PI - ((T)-0.15 * PI)) * u_w;
+        } else if (mode == 2) {
+            // takeoff(): set_desired_states_to_zero (fresh float64 arrays), horizontal position held; t_traj is a
+            // float32 expression (python float - np.float32, NEP 50)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { xd[i] = 0; vd[i] = 0; }
+            xd[0] = x[0]; xd[1] = x[1];
+            ts[8] = (T)__fdiv_rn(__fsub_rn(-0.5f, (float)x[2]), -0.05f);   // (takeoff_end_height - z) / takeoff_velocity
+        } else if (mode == 3) {
+            ts[8] = (T)__fdiv_rn(__fsub_rn(-0.25f, (float)x[2]), 1.0f);    // (landing_motor_cutoff_height - z) / landing_velocity
+        } else if (mode == 4) {
+            // stay(): nothing else
         } else if (mode == 5) {
             ts[8] = (T)0.7 / (T)0.4 + (T)2 * (T)2 * PI / (T)0.4;         // radius / v + num_circles * 2 pi / W
         } else {
             ts[8] = (T)3 * (T)9; ts[6] = (T)0.349066;                   // num_of_eights * T ; eight_w_b1d
         }
     }
-    ts[0] = ts[0] + dt;
+    if (mode != 4) ts[0] = ts[0] + dt;   // update_current_time() is called by every mode function except stay()
     const T t = ts[0];
-    if (mode == 1) {
+    if (mode == 2) {
+        // x_init is the float32 state handed in at the start: "x_init[2] + v t" is float32 arithmetic and "t < t_traj"
+        // a float32 comparison (the python floats are cast, NEP 50)
+        if ((float)t < (float)ts[8]) {
+            xd[2] = (T)__fadd_rn((float)ts[4], (float)((T)-0.05 * t));
+        } else {
+            const T d0 = xd[0] - x[0], d1 = xd[1] - x[1], d2 = xd[2] - x[2];
+            if (N::sqrt(N::fma(d2, d2, N::fma(d1, d1, d0 * d0))) < (T)0.04) {   // waypoint_reached(xd, x, 0.04)
+                xd[2] = (T)-0.5; vd[2] = 0;
+                flags |= 2;   // mark_traj_end(True): manual mode from the next call on
+            }
+        }
+    } else if (mode == 3) {
+        if ((float)t < (float)ts[8]) {
+            xd[2] = (T)__fadd_rn((float)ts[4], (float)((T)1 * t));
+        } else if (x[2] > (T)-0.25) {
+            xd[2] = (T)-0.25; vd[2] = 0;   // mark_traj_end(False): stays in this branch, no manual mode
+        } else {
+            xd[2] = (T)-0.25; vd[2] = (T)1;
+        }
+    } else if (mode == 4) {
+        flags |= 2;   // mark_traj_end(True)
+    } else if (mode == 1) {
         const T k = ts[7], w = ts[6], ek = exp_t<T>(-k * t);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -147,8 +181,12 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
     Wd[0] = 0; Wd[1] = 0; Wd[2] = b3[0] * oc0 + b3[1] * oc1 + b3[2] * oc2;
 }
 
-// reference mode numbers for the goal_mode values of the C ABI (QR_GOAL_TRAJ_HOVER/CIRCLE/EIGHT = 2/3/4)
-QR_DEV int traj_ref_mode(int goal_mode) { return goal_mode == 2 ? 1 : (goal_mode == 3 ? 5 : 6); }
+// reference mode numbers for the goal_mode values of the C ABI:
+// QR_GOAL_TRAJ_HOVER/CIRCLE/EIGHT/TAKEOFF/LAND/STAY = 2/3/4/5/6/7 -> trajectory_generator modes 1/5/6/2/3/4
+QR_DEV int traj_ref_mode(int goal_mode)
+{
+    return goal_mode == 2 ? 1 : (goal_mode == 3 ? 5 : (goal_mode == 4 ? 6 : (goal_mode == 5 ? 2 : (goal_mode == 6 ? 3 : 4))));
+}
 
 // trajectory start from the float32-cast state (main.py:226-228): mark_traj_start + the first get_desired
 template <typename T>

@@ -177,7 +177,7 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     if (c->n_envs >= ((int64_t)1 << 31)) return fail(QR_ERR_INVALID, "qr_create: n_envs must be below 2^31 per handle");
     if (c->integrator == QR_INT_EULER && c->mode != QR_MODE_QUAD)
         return fail(QR_ERR_INVALID, "qr_create: the Euler integrator exists only for the base Quad-v0 env (quad.py:252)");
-    if (c->goal_mode < QR_GOAL_EXTERNAL || c->goal_mode > QR_GOAL_TRAJ_EIGHT) return fail(QR_ERR_INVALID, "qr_create: bad goal_mode");
+    if (c->goal_mode < QR_GOAL_EXTERNAL || c->goal_mode > QR_GOAL_TRAJ_STAY) return fail(QR_ERR_INVALID, "qr_create: bad goal_mode");
     if (c->goal_mode != QR_GOAL_EXTERNAL && c->mode == QR_MODE_QUAD)
         return fail(QR_ERR_INVALID, "qr_create: on-device goal generation needs a wrapper mode");
     int ndev = 0;

@@ -46,7 +46,8 @@ class BatchedQuadEnv:
         cfg.n_envs = int(num_envs); cfg.env_id_offset = int(env_id_offset); cfg.seed = int(seed)
         cfg.autoreset = int(bool(autoreset))
         cfg.goal_mode = {"external": nat.GOAL_EXTERNAL, "traj0": nat.GOAL_TRAJ_MODE0, "hover": nat.GOAL_TRAJ_HOVER,
-                         "circle": nat.GOAL_TRAJ_CIRCLE, "eight": nat.GOAL_TRAJ_EIGHT}[goal_mode]
+                         "circle": nat.GOAL_TRAJ_CIRCLE, "eight": nat.GOAL_TRAJ_EIGHT, "takeoff": nat.GOAL_TRAJ_TAKEOFF,
+                         "land": nat.GOAL_TRAJ_LAND, "stay": nat.GOAL_TRAJ_STAY}[goal_mode]
         cfg.env_type = nat.ENV_TRAIN if env_type == "train" else nat.ENV_EVAL
         cfg.max_episode_steps = int(max_episode_steps)
         cfg.diagnostics = int(bool(diagnostics))

@@ -40,8 +40,10 @@ enum { QR_MODE_QUAD = 0, QR_MODE_COUPLED = 1, QR_MODE_DECOUPLED = 2 };   /* Quad
 enum { QR_F32 = 0, QR_F64 = 1 };
 enum { QR_INT_DOP853 = 0, QR_INT_EULER = 1 };                            /* quad.py:62 */
 enum { QR_ENV_TRAIN = 0, QR_ENV_EVAL = 1 };                              /* reset(env_type=...) quad.py:171 */
-/* set_goal_state | on-device trajectory_generator: mode 0 (idle, evaluated inside qr_step), 1 hover, 5 circle, 6 figure eight */
-enum { QR_GOAL_EXTERNAL = 0, QR_GOAL_TRAJ_MODE0 = 1, QR_GOAL_TRAJ_HOVER = 2, QR_GOAL_TRAJ_CIRCLE = 3, QR_GOAL_TRAJ_EIGHT = 4 };
+/* set_goal_state | on-device trajectory_generator: mode 0 (idle, evaluated inside qr_step), 1 hover, 5 circle, 6 figure
+ * eight, 2 take-off, 3 land, 4 stay (utils/trajectory_generator.py:113-173, 252-505) */
+enum { QR_GOAL_EXTERNAL = 0, QR_GOAL_TRAJ_MODE0 = 1, QR_GOAL_TRAJ_HOVER = 2, QR_GOAL_TRAJ_CIRCLE = 3, QR_GOAL_TRAJ_EIGHT = 4,
+       QR_GOAL_TRAJ_TAKEOFF = 5, QR_GOAL_TRAJ_LAND = 6, QR_GOAL_TRAJ_STAY = 7 };
 /* per-env status bits (the reference raises / ignores sol.status instead: coupled:63-64) */
 enum { QR_ST_NONFINITE = 1, QR_ST_TOO_SMALL_STEP = 2, QR_ST_SVD = 4 };
 /* indices into the 16-double statistics vector of qr_stats */
@@ -113,8 +115,8 @@ int qr_reset(qr_handle* h, const uint8_t* mask, int env_type, void* stream);
 int qr_init_goal(qr_handle* h, const uint8_t* mask, void* stream);
 
 /* trajectory_generator.get_desired(env.get_current_state(), mode) + env.set_goal_state, called by the trainer before
- * every step (main.py:145-147), for goal_mode HOVER / CIRCLE / EIGHT (utils/trajectory_generator.py:252-277,359-505,
- * manual fallback 232-249).  No-op for external goals and for mode 0. */
+ * every step (main.py:145-147), for goal_mode HOVER / CIRCLE / EIGHT / TAKEOFF / LAND / STAY
+ * (utils/trajectory_generator.py:252-505, manual fallback 232-249).  No-op for external goals and for mode 0. */
 int qr_goal_update(qr_handle* h, void* stream);
 
 /* env.get_norm_error_state(framework) (quad.py:421-466): writes obs from the CURRENT state and goal and,

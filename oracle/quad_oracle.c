@@ -357,8 +357,8 @@ int qo_traj_start_f64(int64_t n, const double* state, double* ts)
     return 0;
 }
 
-/* One get_desired(state, mode) call (trajectory_generator.py:113-173) for mode 1 (hover), 5 (circle), >= 6 (figure
- * eight).  goal[n][12] = xd vd b1d Wd is read and updated in place (several branches leave components untouched).
+/* One get_desired(state, mode) call (trajectory_generator.py:113-173) for mode 1 (hover), 2 (take-off), 3 (land),
+ * 4 (stay), 5 (circle), >= 6 (figure eight).  goal[n][12] = xd vd b1d Wd is read and updated in place (several branches leave components untouched).
  * numpy detail that is part of the observable behaviour: set_desired_states_to_current makes xd / vd COPIES of the
  * state's x / v (:212-215); under main.py's protocol the trajectory starts from the float32 reset state
  * (main.py:226-228), so xd and vd are float32 arrays for the whole trajectory and every element assignment rounds
@@ -437,6 +437,53 @@ int qo_traj_desired_f64(int mode, int64_t n, const double* state, double* ts, do
             } else {
                 flags |= 2;   /* mark_traj_end(True): manual mode from the next call on */
             }
+        } else if (mode == 2) {   /* takeoff :280-309 */
+            /* set_desired_states_to_zero makes xd / vd fresh FLOAT64 arrays; x_init is the (float32) state handed in
+             * at the start, so "x_init[2] + takeoff_velocity * t" and t_traj are float32 expressions (NEP 50: the
+             * python-float operand is cast to float32), and "t < t_traj" compares in float32. */
+            const double takeoff_end_height = -0.5, takeoff_velocity = -0.05;   /* :82-83 */
+            if (!(flags & 1)) {
+                for (int i = 0; i < 3; ++i) { xd[i] = 0.0; vd[i] = 0.0; s[2 + i] = x[i]; }
+                xd[0] = x[0]; xd[1] = x[1];
+                s[8] = (double)(((float)takeoff_end_height - (float)x[2]) / (float)takeoff_velocity);
+                b1d[0] = cos(th_cur); b1d[1] = sin(th_cur); b1d[2] = 0.0;
+                flags |= 1;
+            }
+            s[0] = s[0] + dt;
+            const double t = s[0];
+            if ((float)t < (float)s[8]) {
+                xd[2] = (double)((float)s[4] + (float)(takeoff_velocity * t));
+            } else {
+                const double d0 = xd[0] - x[0], d1 = xd[1] - x[1], d2 = xd[2] - x[2];
+                if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) < 0.04) {   /* waypoint_reached(xd, x, 0.04) */
+                    xd[2] = takeoff_end_height; vd[2] = 0.0;
+                    flags |= 2;   /* mark_traj_end(True) */
+                }
+            }
+        } else if (mode == 3) {   /* land :322-349 */
+            const double landing_velocity = 1.0, cutoff = -0.25;   /* :86-87 */
+            if (!(flags & 1)) {
+                for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; s[2 + i] = x[i]; }
+                s[8] = (double)(((float)cutoff - (float)x[2]) / (float)landing_velocity);
+                b1d[0] = cos(th_cur); b1d[1] = sin(th_cur); b1d[2] = 0.0;
+                flags |= 1;
+            }
+            s[0] = s[0] + dt;
+            const double t = s[0];
+            if ((float)t < (float)s[8]) {
+                xd[2] = (double)((float)s[4] + (float)(landing_velocity * t));
+            } else if (x[2] > cutoff) {
+                xd[2] = cutoff; vd[2] = 0.0;   /* mark_traj_end(False): no manual mode; the branch repeats */
+            } else {
+                xd[2] = cutoff; vd[2] = F32(landing_velocity);
+            }
+        } else if (mode == 4) {   /* stay :352-357: no clock update; manual mode from the next call on */
+            if (!(flags & 1)) {
+                for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; s[2 + i] = x[i]; }
+                b1d[0] = cos(th_cur); b1d[1] = sin(th_cur); b1d[2] = 0.0;
+                flags |= 1;
+            }
+            flags |= 2;
         } else {   /* eight_shaped_curve :415-505 */
             if (!(flags & 1)) {
                 for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; s[2 + i] = x[i]; }

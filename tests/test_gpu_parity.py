@@ -416,9 +416,10 @@ def test_status_flags_nonfinite_state():
     env.close()
 
 
-@pytest.mark.parametrize("name,gm", [("hover", "hover"), ("circle", "circle"), ("eight", "eight"), ("circle_manual", "circle")])
+@pytest.mark.parametrize("name,gm", [("hover", "hover"), ("circle", "circle"), ("eight", "eight"), ("circle_manual", "circle"),
+                                     ("takeoff", "takeoff"), ("land", "land"), ("land_low", "land"), ("stay", "stay")])
 def test_trajectory_modes_match_reference(name, gm):
-    """qr_init_goal + qr_goal_update (modes 1 / 5 / 6 and the manual fallback) call by call against the reference's
+    """qr_init_goal + qr_goal_update (modes 1 - 6 and the manual fallback) call by call against the reference's
     TrajectoryGenerator driven along a real flight (tests/golden/traj_modes.npz)."""
     g = _load("traj_modes.npz")
     st, goal_ref, bdd_ref, t_ref = g[name + "_state"], g[name + "_goal"], g[name + "_b1d_dot"], g[name + "_t"]

@@ -160,7 +160,8 @@ def test_device_reset_matches_oracle(twin):
         assert np.abs(st - st_o).max() <= 1e-14 and np.abs(par - par_o).max() <= 1e-15 and (ig == 0).all()
 
 
-@pytest.mark.parametrize("name,mode", [("hover", 1), ("circle", 5), ("eight", 6), ("circle_manual", 5)])
+@pytest.mark.parametrize("name,mode", [("hover", 1), ("circle", 5), ("eight", 6), ("circle_manual", 5), ("takeoff", 2), ("land", 3),
+                                       ("land_low", 3), ("stay", 4)])
 def test_device_trajectory_modes_match_reference(twin, name, mode):
     """traj_start / traj_desired call by call against the reference's TrajectoryGenerator (tests/golden/traj_modes.npz)."""
     g = np.load(os.path.join(G, "traj_modes.npz"))

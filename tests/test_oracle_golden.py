@@ -176,16 +176,17 @@ def test_trajgen_mode0_matches_reference():
     assert np.abs(b1d_again - g["goal"][~ok, 6:9]).max() < 1e-12
 
 
-@pytest.mark.parametrize("name,mode", [("hover", 1), ("circle", 5), ("eight", 6), ("circle_manual", 5)])
+@pytest.mark.parametrize("name,mode", [("hover", 1), ("circle", 5), ("eight", 6), ("circle_manual", 5), ("takeoff", 2), ("land", 3),
+                                       ("land_low", 3), ("stay", 4)])
 def test_trajgen_modes_match_reference(name, mode):
-    """Modes 1 / 5 / 6 and the manual fallback, call by call against the reference's TrajectoryGenerator
+    """Modes 1 - 6 and the manual fallback, call by call against the reference's TrajectoryGenerator
     (the hover's two random draws are injected from the reference run)."""
     g = _load("traj_modes.npz")
     st, goal_ref, bdd_ref, t_ref = g[name + "_state"], g[name + "_goal"], g[name + "_b1d_dot"], g[name + "_t"]
     t_traj, w, smooth, theta0 = g[name + "_draws"]
     draws = np.array([[(t_traj - 2.0) / 3.0, (w + 0.15 * np.pi) / (0.3 * np.pi)]])
     ts = qo.traj_start(st[0:1])
-    if name != "circle_manual":          # manual() overwrites theta_init with the heading at the switch
+    if not bool(g[name + "_manual"][-1]):   # manual() overwrites theta_init with the heading at the switch
         assert abs(ts[0, 5] - theta0) < 1e-15
     goal = np.zeros((1, 12)); goal[0, 6] = 1.0
     worst = 0.0
