@@ -133,10 +133,14 @@ template <typename T> QR_DEV void ks_load_lane(const T* col, int lane, T* k)
 // slot, `lane8` = lane * 8): explicit ld.shared with immediate offsets, so the loop needs one add per K vector.
 QR_DEV void ks_load_lane_sa(unsigned sa, unsigned lane8, float* k)
 {
+#if QR_PTX
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(k[0]), "=f"(k[1]), "=f"(k[2]), "=f"(k[3]) : "r"(sa) : "memory");
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+512];" : "=f"(k[4]), "=f"(k[5]), "=f"(k[6]), "=f"(k[7]) : "r"(sa) : "memory");
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+1024];" : "=f"(k[8]), "=f"(k[9]), "=f"(k[10]), "=f"(k[11]) : "r"(sa) : "memory");
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+1536];" : "=f"(k[12]), "=f"(k[13]) : "r"(sa - lane8) : "memory");
+#else
+    (void)sa; (void)lane8; (void)k;   // host builds take the generic-pointer loader (see dop853_attempt)
+#endif
 }
 QR_DEV void ks_load_lane_sa(unsigned, unsigned, double*) {}   // float64 uses the generic-pointer loader
 
@@ -342,11 +346,9 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
             axpy14_out<T>(ha0, K0, y, ys);
         }
         // couplings A[s][j], j >= 1, from the flattened table (constant bank, uniform datapath)
-        // (measured and dropped: two K vectors per trip / software pipelining -- the extra registers cost more
-        //  than the exposed LDS latency, profiles/r01_summary.md)
 #if QR_PIPE
         // two K vectors in flight: the loads of the next one are issued before the sums of the current one
-        if (sizeof(T) == 4) {
+        if (QR_PTX && sizeof(T) == 4) {
             int p = TB::Ps(s);
             int n = TB::Ps(s + 1) - p;
             if (n > 0) {
@@ -376,7 +378,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
                 const TabEntry<T> te = TB::P(p);
                 const T c = h * te.c;
                 T k[14];
-                if (sizeof(T) == 4) ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, k);
+                if (QR_PTX && sizeof(T) == 4) ks_load_lane_sa(kl_sa + (unsigned)te.off, (unsigned)lane * 8u, k);
                 else ks_load_lane<T>(reinterpret_cast<const T*>(reinterpret_cast<const char*>(kl) + te.off), lane, k);
                 axpy14<T>(c, k, ys);
             }

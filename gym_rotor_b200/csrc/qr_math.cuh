@@ -9,6 +9,13 @@
 #include <math.h>
 
 #define QR_DEV __device__ __forceinline__
+// PTX is only emitted in device passes; the host pass of nvcc -- and tests/host_twin, which compiles these headers
+// with g++ to unit-test the arithmetic without a GPU -- sees plain C for the few inline-PTX helpers
+#ifdef __CUDA_ARCH__
+#define QR_PTX 1
+#else
+#define QR_PTX 0
+#endif
 
 namespace qr {
 
@@ -27,11 +34,19 @@ template <> struct num<float> {
     static QR_DEV float ulp_up(float t) { return __int_as_float(__float_as_int(t) + 1) - t; }
     static QR_DEV float inf() { return __int_as_float(0x7f800000); }
     // x^(1/8) and x^(-1/8) by square-root chains: <= 2 ulp, no transcendental (only scales the step size)
+#if QR_PTX
     static QR_DEV float asqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+    static QR_DEV float asqrt(float x) { return sqrtf(x); }
+#endif
     static QR_DEV float root8(float x) { return asqrt(asqrt(asqrt(x))); }
     static QR_DEV float inv_root8(float x) { return rsqrtf(asqrt(asqrt(x))); }
     // reciprocal of an error scale (feeds norms that only steer the step size): MUFU.RCP, <= 1 ulp
+#if QR_PTX
     static QR_DEV float recip(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+    static QR_DEV float recip(float x) { return 1.0f / x; }
+#endif
     static constexpr float eps_jacobi = 1e-7f;
     static constexpr float huge = 3.0e38f;
 };

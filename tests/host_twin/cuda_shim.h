@@ -1,7 +1,7 @@
 // cuda_shim.h -- TEST INFRASTRUCTURE.  Lets g++ compile the per-env device functions of gym_rotor_b200/csrc/*.cuh
 // for the HOST so that they can be unit-tested against the golden vectors without a GPU (tests/test_host_twin.py).
-// Only the float64 instantiations are exercised (the float32 ones use sm_100a PTX).  Nothing in the package loads
-// this: the product has no CPU path.
+// float64 and float32 instantiations (the headers' few inline-PTX helpers fall back to plain C outside device passes,
+// QR_PTX in qr_math.cuh).  Nothing in the package loads this: the product has no CPU path.
 #pragma once
 #ifdef __CUDACC__
 #error "host-only shim"

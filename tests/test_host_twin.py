@@ -35,6 +35,7 @@ def twin(tmp_path_factory):
     L = C.CDLL(out)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     L.tw_step.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, C.c_int, dp, dp, C.POINTER(C.c_float), dp, ip, ip, ip]
+    L.tw_step_f32.argtypes = L.tw_step.argtypes
     L.tw_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, dp, dp, dp, dp]
     L.tw_traj_start.argtypes = [dp, dp, dp]
     L.tw_traj_desired.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double]
@@ -55,8 +56,9 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def _step_rows(L, cfg, state, integ, params, goal, action, a32):
+def _step_rows(L, cfg, state, integ, params, goal, action, a32, f32=False):
     n = state.shape[0]
+    step = L.tw_step_f32 if f32 else L.tw_step
     O = 23 if cfg.mode == 1 else 18
     st = np.empty((n, 18)); ig = np.empty((n, 8)); obs = np.empty((n, O), np.float32)
     rew = np.empty((n, 2)); dn = np.empty((n, 2), np.int32); nfev = np.empty(n, np.int32); nproj = np.empty(n, np.int32)
@@ -65,7 +67,7 @@ def _step_rows(L, cfg, state, integ, params, goal, action, a32):
     for i in range(n):
         s_i, g_i = np.ascontiguousarray(state[i], np.float64), np.ascontiguousarray(integ[i], np.float64)
         p_i, a_i = np.ascontiguousarray(params[i], np.float64), np.ascontiguousarray(action[i], np.float64)
-        status[i] = L.tw_step(C.byref(cfg), _dp(s_i), _dp(g_i), _dp(p_i), _dp(goal[i]), _dp(a_i), int(a32),
+        status[i] = step(C.byref(cfg), _dp(s_i), _dp(g_i), _dp(p_i), _dp(goal[i]), _dp(a_i), int(a32),
                               _dp(st[i]), _dp(ig[i]), obs[i].ctypes.data_as(C.POINTER(C.c_float)), _dp(rew[i]),
                               dn[i].ctypes.data_as(C.POINTER(C.c_int)), nfev[i:i + 1].ctypes.data_as(C.POINTER(C.c_int)),
                               nproj[i:i + 1].ctypes.data_as(C.POINTER(C.c_int)))
@@ -93,6 +95,24 @@ def test_device_functions_match_reference_golden(twin, fw, tag, a32):
     assert (dn[:, :G_].astype(bool) == g["done"]).all()
     assert (nfev == g["nfev"]).all()
     assert np.abs(rew[:, :G_] - g["reward"]).max() <= 2e-7 and (rew[:, :G_] != g["reward"]).mean() <= 5e-3
+    assert int(status.max()) == 0
+
+
+@pytest.mark.parametrize("fw,tag", [("MONO", "mono"), ("MODUL", "modul")])
+def test_device_functions_float32_within_1e5_of_reference(twin, fw, tag):
+    """The float32 instantiations (packed stage sums, reciprocal multiplies, float32 reward norms; exact 1/x and sqrt in
+    place of the MUFU approximations) with the tolerances of test_gpu_parity.py::test_fp32_step_within_1e5_of_reference."""
+    g = np.load(os.path.join(G, "step_%s_a64.npz" % tag))
+    cfg = _config(1 if fw == "MONO" else 2)
+    act = g["action"].astype(np.float32).astype(np.float64)
+    st, ig, obs, rew, dn, nfev, status, _ = _step_rows(twin, cfg, g["state_in"], g["integ_in"], g["params"], g["goal"], act, True, f32=True)
+    assert np.abs(st - g["state_out"]).max() <= 1e-5
+    assert np.abs(ig - g["integ_out"]).max() <= 1e-5
+    assert np.abs(obs - g["obs"]).max() <= 1e-5
+    G_ = g["done"].shape[1]
+    assert np.abs(rew[:, :G_] - g["reward"]).max() <= 1e-4
+    assert (dn[:, :G_].astype(bool) != g["done"]).mean() <= 2e-3
+    assert ((nfev - 2) // 12 != (g["nfev"] - 2) // 12).mean() <= 0.03
     assert int(status.max()) == 0
 
 
