@@ -83,17 +83,28 @@ template <typename T> QR_DEV void store_params_goal(const EnvRegs<T>& r, const S
     }
 }
 
+#if QR_PTX
 QR_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else   // host pass / tests/host_twin (see QR_PTX in qr_math.cuh)
+QR_DEV void prefetch_l2(const void*) {}
+#endif
 
 // global -> shared without a register in between (LDGSTS); completion is awaited by the issuing thread
+#if QR_PTX
 template <int BYTES> QR_DEV void cp_async(void* smem, const void* gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "n"(BYTES) : "memory");
 }
-template <typename T> QR_DEV int32_t& stash_i32(T* sh, int slot) { return *reinterpret_cast<int32_t*>(sh + slot * 32); }
 QR_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 QR_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> QR_DEV void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else   // host pass / tests/host_twin: the copy happens at once, the waits are no-ops
+template <int BYTES> QR_DEV void cp_async(void* smem, const void* gmem) { memcpy(smem, gmem, BYTES); }
+QR_DEV void cp_async_wait_all() {}
+QR_DEV void cp_async_commit() {}
+template <int N> QR_DEV void cp_async_wait_group() {}
+#endif
+template <typename T> QR_DEV int32_t& stash_i32(T* sh, int slot) { return *reinterpret_cast<int32_t*>(sh + slot * 32); }
 
 QR_DEV double warp_sum(double v)
 {

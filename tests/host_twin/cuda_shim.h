@@ -32,7 +32,9 @@ static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; 
 static inline double __longlong_as_double(long long v) { double f; memcpy(&f, &v, 8); return f; }
 static inline long long __double_as_longlong(double f) { long long v; memcpy(&v, &f, 8); return v; }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
-// (__sincosf / __expf: glibc declares functions of these names; the float32 paths that use them are not exercised)
+// glibc declares (internal) functions of these names: map the CUDA fast-math intrinsics with macros instead
+#define __sincosf(a, s, c) sincosf(a, s, c)
+#define __expf(a) expf(a)
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 static inline size_t __cvta_generic_to_shared(const void*) { return 0; }

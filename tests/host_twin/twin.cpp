@@ -178,6 +178,24 @@ extern "C" {
 int tw_step(TW_ARGS) { return step_one<double>(TW_PASS); }
 int tw_step_f32(TW_ARGS) { return step_one<float>(TW_PASS); }
 
+// env.get_norm_error_state(): observation from state + goal, integral errors advanced once (in place)
+void tw_norm_error_state(const qr_config* cfg, const double* state, double* integ_io, const double* goal, float* obs_out)
+{
+    const EnvConst<double> c = make_const<double>(*cfg);
+    EnvRegs<double> r;
+    memset(&r, 0, sizeof(r));
+    for (int i = 0; i < 3; ++i) { r.x[i] = state[i]; r.y[i] = state[3 + i]; }
+    for (int i = 0; i < 9; ++i) r.y[3 + i] = state[6 + i];
+    r.y[12] = state[15]; r.y[13] = state[16]; r.W3 = state[17];
+    for (int i = 0; i < 8; ++i) r.I[i] = integ_io[i];
+    for (int i = 0; i < 12; ++i) r.goal[i] = goal[i];
+    float o[23];
+    norm_error_state<double>(r, c, o, c.mode);
+    for (int i = 0; i < 8; ++i) integ_io[i] = r.I[i];
+    const int O = (c.mode == 1) ? 23 : 18;
+    for (int i = 0; i < O; ++i) obs_out[i] = o[i];
+}
+
 // env.reset(env_type) for global env id `gid`, episode index `episode` (+ the mode-0 goal when goal_mode == 1)
 void tw_reset(const qr_config* cfg, uint64_t gid, uint32_t episode, int env_type, double* state_out, double* integ_out,
               double* params_out, double* goal_out)

@@ -1,0 +1,274 @@
+"""The REAL step kernel, run WITHOUT a GPU.
+
+tests/host_twin/twin_kernel.cpp compiles qr::k_step itself (gym_rotor_b200/csrc/qr_kernels.cuh: the per-lane state
+machine, the shared-memory stash, the fetch-ahead of the next env, the reset queue and the parked reset call, both
+observation paths, the statistics) for the host and runs it on the one-warp SIMT emulator of tests/host_twin/simt.h
+(32 fibers, every warp collective a rendezvous; a collective that not all lanes reach aborts as a deadlock).  These
+tests drive it over host arrays laid out like the device buffers, against the reference's golden vectors and against
+the per-env functions of tests/host_twin/twin.cpp.  Test infrastructure only: the package never loads the twin and
+has no CPU path; timing and the float32 MUFU approximations remain GPU-only matters (tests/test_gpu_parity.py).
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+TWIN_DIR = os.path.join(ROOT, "tests", "host_twin")
+CUDA_INC = "/usr/local/cuda/include"
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")),
+                                reason="needs g++ and the CUDA headers")
+
+
+class TwArrays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("state", "integ", "params", "goal", "traj", "obs", "reward", "done", "terminated",
+                                          "truncated", "final_obs", "nfev", "status", "ep_return", "ep_length", "ep_index",
+                                          "stats", "actions")] + [("act_f32", C.c_int)] + \
+               [(n, C.c_void_p) for n in ("obs_roll", "reward_roll", "done_roll")]
+
+
+def _build(src, tmp, name, opt="-O1"):
+    out = os.path.join(tmp, name)
+    cmd = ["g++", "-std=c++17", opt, "-ffp-contract=off", "-fPIC", "-shared", "-I" + CUDA_INC, "-I" + TWIN_DIR,
+           "-I" + os.path.join(ROOT, "gym_rotor_b200", "csrc"), "-o", out, os.path.join(TWIN_DIR, src)]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    return C.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def libs(tmp_path_factory):
+    tmp = str(tmp_path_factory.mktemp("twink"))
+    K = _build("twin_kernel.cpp", tmp, "libtwink.so")
+    K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int]
+    F = _build("twin.cpp", tmp, "libtwin.so", "-O2")
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    F.tw_step.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, C.c_int, dp, dp, C.POINTER(C.c_float), dp, ip, ip, ip]
+    F.tw_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, dp, dp, dp, dp]
+    F.tw_norm_error_state.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_float)]
+    return K, F
+
+
+def _config(mode, dtype64=True, **kw):
+    from gym_rotor_b200 import _native as nat
+    cfg = nat.QrConfig()
+    nat.check(nat.load().qr_default_config(C.byref(cfg), mode, nat.F64 if dtype64 else nat.F32))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+class HostEnv:
+    """Host arrays with the layout of qr_buffers + one emulated k_step launch per call."""
+
+    def __init__(self, K, cfg, warps=3):
+        self.K, self.cfg, self.warps = K, cfg, warps
+        n = self.n = int(cfg.n_envs)
+        self.T = np.float64 if cfg.dtype == 1 else np.float32
+        self.O = 23 if cfg.mode == 1 else 18
+        self.A = 5 if cfg.mode == 2 else 4
+        self.G = 2 if cfg.mode == 2 else 1
+        T = self.T
+        self.state = np.zeros((18, n), T); self.state[6] = 1; self.state[10] = 1; self.state[14] = 1
+        self.integ = np.zeros((8, n), T); self.params = np.zeros((6, n), T); self.goal = np.zeros((12, n), T); self.goal[6] = 1
+        self.traj = np.zeros((12, n), T)
+        self.obs = np.zeros((n, self.O), np.float32); self.final_obs = np.zeros((n, self.O), np.float32)
+        self.reward = np.zeros((n, self.G), T); self.done = np.zeros((n, self.G), np.uint8)
+        self.terminated = np.zeros(n, np.uint8); self.truncated = np.zeros(n, np.uint8)
+        self.nfev = np.zeros(n, np.int32); self.status = np.zeros(n, np.uint8)
+        self.ep_return = np.zeros((2, n), T); self.ep_length = np.zeros(n, np.int32); self.ep_index = np.zeros(n, np.uint32)
+        self.stats = np.zeros(16, np.float64)
+
+    def set_state(self, st, ig, par, goal):          # [n,18] [n,8] [n,6] [n,12] like vec_env.set_state
+        self.state[:] = np.asarray(st).T; self.integ[:] = np.asarray(ig).T
+        self.params[:] = np.asarray(par).T; self.goal[:] = np.asarray(goal).T
+
+    def launch(self, actions=None, n_steps=1, store=False):
+        b = TwArrays()
+        keep = []
+        for name in ("state", "integ", "params", "goal", "traj", "obs", "reward", "done", "terminated", "truncated", "final_obs",
+                     "nfev", "status", "ep_return", "ep_length", "ep_index", "stats"):
+            setattr(b, name, getattr(self, name).ctypes.data)
+        if actions is not None:
+            actions = np.ascontiguousarray(actions)
+            assert actions.dtype in (np.float32, np.float64) and actions.shape[-2:] == (self.n, self.A)
+            keep.append(actions)
+            b.actions = actions.ctypes.data; b.act_f32 = int(actions.dtype == np.float32)
+        out = None
+        if store:
+            out = (np.zeros((n_steps, self.n, self.O), np.float32), np.zeros((n_steps, self.n, self.G), self.T),
+                   np.zeros((n_steps, self.n, self.G), np.uint8))
+            b.obs_roll, b.reward_roll, b.done_roll = (x.ctypes.data for x in out)
+        rc = self.K.tw_kstep(C.byref(self.cfg), C.byref(b), 0, self.n, int(n_steps), self.warps)
+        assert rc == 0
+        return out
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("fw,tag,a32", [("MONO", "mono", False), ("MONO", "mono", True),
+                                        ("MODUL", "modul", False), ("MODUL", "modul", True)])
+def test_kernel_fp64_step_matches_reference_golden(libs, fw, tag, a32):
+    """test_gpu_parity.py::test_fp64_step_matches_reference_golden on the emulated kernel."""
+    K, _ = libs
+    g = np.load(os.path.join(G, "step_%s_%s.npz" % (tag, "a32" if a32 else "a64")))
+    n = g["action"].shape[0]
+    env = HostEnv(K, _config(1 if fw == "MONO" else 2, n_envs=n))
+    env.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
+    env.launch(g["action"].astype(np.float32 if a32 else np.float64))
+    assert _relerr(env.state.T, g["state_out"]) <= 1e-12
+    assert np.abs(env.integ.T - g["integ_out"]).max() <= 1e-12
+    flips = int((env.obs.view(np.uint32) != g["obs"].view(np.uint32)).sum())
+    assert flips <= 3, flips
+    assert (env.done.astype(bool) == g["done"]).all()
+    assert (env.nfev == g["nfev"]).all()
+    assert np.abs(env.reward - g["reward"]).max() <= 2e-7
+    assert int(env.status.max()) == 0 and env.stats[7] == n
+
+
+@pytest.mark.parametrize("fw,tag", [("MONO", "mono"), ("MODUL", "modul")])
+def test_kernel_fp32_step_within_1e5(libs, fw, tag):
+    K, _ = libs
+    g = np.load(os.path.join(G, "step_%s_a64.npz" % tag))
+    n = g["action"].shape[0]
+    env = HostEnv(K, _config(1 if fw == "MONO" else 2, dtype64=False, n_envs=n), warps=12)
+    env.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
+    env.launch(g["action"].astype(np.float32))
+    assert np.abs(env.state.T - g["state_out"]).max() <= 1e-5
+    assert np.abs(env.obs - g["obs"]).max() <= 1e-5
+    assert (env.done.astype(bool) != g["done"]).mean() <= 2e-3
+    assert ((env.nfev - 2) // 12 != (g["nfev"] - 2) // 12).mean() <= 0.03
+
+
+@pytest.mark.parametrize("integ", ["solve_ivp", "euler"])
+def test_kernel_quad_v0_base_env(libs, integ):
+    K, _ = libs
+    g = np.load(os.path.join(G, "quad_v0.npz"))
+    s_in = g[integ + "_state_in"]; n = s_in.shape[0]
+    env = HostEnv(K, _config(0, n_envs=n, integrator=1 if integ == "euler" else 0))
+    env.set_state(s_in, np.zeros((n, 8)), g[integ + "_params"], g[integ + "_goal"])
+    env.launch(np.ascontiguousarray(g[integ + "_action"], np.float64))
+    assert np.abs(env.state.T - g[integ + "_state_out"]).max() < 1e-12
+    assert (env.done.astype(bool) == g[integ + "_done"]).all()
+    assert np.abs(env.reward - g[integ + "_reward"]).max() < 1e-12
+
+
+def test_kernel_extreme_angular_rates_take_the_checked_redo(libs):
+    """|W| far outside the termination limits: stage matrices leave SO(3), the speculative attempt is thrown away and
+    redone with per-stage re-projection; results and RHS counts must equal the oracle's stage-by-stage evaluation."""
+    import quad_oracle as qo
+    K, _ = libs
+    n = 128
+    rng = np.random.default_rng(0)
+    orc = qo.COracle("MONO")
+    st, ig, par = orc.reset_from_uniforms(rng.random((n, 20)))
+    st[:, 15:18] = rng.uniform(-1, 1, (n, 3)) * 60.0
+    goal = np.zeros((n, 12)); goal[:, 6] = 1.0
+    act = rng.uniform(-1, 1, (n, 4))
+    env = HostEnv(K, _config(1, n_envs=n))
+    env.set_state(st, ig, par, goal)
+    env.launch(act)
+    st_o, ig_o = st.copy(), ig.copy()
+    obs_o, rew_o, done_o, nfev_o, status_o = orc.step(st_o, ig_o, par, goal, act)
+    assert (env.nfev == nfev_o).all()
+    assert _relerr(env.state.T, st_o) <= 1e-11
+    assert env.stats[15] > 0          # SO(3) re-projections were needed
+
+
+def _reset_all(F, cfg, env, episode=1):
+    """k_reset + k_init_goal for every env, through the per-env functions of twin.cpp."""
+    n = env.n
+    st = np.empty((n, 18)); ig = np.empty((n, 8)); par = np.empty((n, 6)); gl = np.empty((n, 12))
+    dp = C.POINTER(C.c_double)
+    for i in range(n):
+        F.tw_reset(C.byref(cfg), cfg.env_id_offset + i, episode, cfg.env_type, st[i].ctypes.data_as(dp), ig[i].ctypes.data_as(dp),
+                   par[i].ctypes.data_as(dp), gl[i].ctypes.data_as(dp))
+    env.set_state(st, ig, par, gl)
+    env.ep_index[:] = episode
+    return st, ig, par, gl
+
+
+@pytest.mark.parametrize("dtype64", [True, False])
+def test_kernel_rollout_with_autoreset_equals_single_steps(libs, dtype64):
+    """Multi-step launch (reset at the parked call site, env stays in its lane) == single-step launches (queued resets,
+    batches of >= 24 and bursts of a common time limit), ragged n, misaligned rollout rows."""
+    K, F = libs
+    n, steps = 203, 20
+    kw = dict(n_envs=n, seed=5, autoreset=1, goal_mode=1, max_episode_steps=7)
+    c1, c2 = _config(1, dtype64, **kw), _config(1, dtype64, **kw)
+    e1, e2 = HostEnv(K, c1, warps=2), HostEnv(K, c2, warps=5)
+    _reset_all(F, c1, e1); _reset_all(F, c2, e2)
+    rng = np.random.default_rng(15)
+    acts = rng.uniform(-1, 1, (steps, n, 4)).astype(np.float64 if dtype64 else np.float32)
+    obs_r, rew_r, done_r = e1.launch(acts, n_steps=steps, store=True)
+    for k in range(steps):
+        e2.launch(acts[k])
+        assert np.array_equal(e2.obs, obs_r[k]), k
+        assert np.array_equal(e2.reward, rew_r[k]) and np.array_equal(e2.done, done_r[k])
+    for name in ("state", "integ", "params", "goal", "obs", "ep_length", "ep_index"):
+        assert np.array_equal(getattr(e1, name), getattr(e2, name)), name
+    assert e1.stats[0] == e2.stats[0] >= 2 * n and e1.stats[7] == e2.stats[7] == steps * n
+
+
+def test_kernel_autoreset_equals_manual_protocol(libs):
+    """The kernel's auto reset against step -> reset -> goal -> get_norm_error_state done env by env with the per-env
+    functions (main.py:212-230): states, goals, parameters, first observations of the new episodes, final_obs."""
+    K, F = libs
+    n, steps, limit = 96, 30, 9
+    cfg = _config(1, n_envs=n, seed=3, autoreset=1, goal_mode=1, max_episode_steps=limit)
+    ref_cfg = _config(1, n_envs=n, seed=3, autoreset=0, goal_mode=1)
+    env = HostEnv(K, cfg, warps=1)
+    st, ig, par, gl = _reset_all(F, cfg, env)
+    episode = np.ones(n, np.int64); eplen = np.zeros(n, np.int64)
+    rng = np.random.default_rng(9)
+    dp, ip, fp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_float)
+    n_resets = 0
+    for t in range(steps):
+        act = rng.uniform(-1, 1, (n, 4))
+        env.launch(act)
+        for i in range(n):
+            so = np.empty(18); io = np.empty(8); ob = np.empty(23, np.float32); rw = np.empty(2); dn = np.empty(2, np.int32)
+            nf = np.empty(1, np.int32); npj = np.empty(1, np.int32)
+            F.tw_step(C.byref(ref_cfg), st[i].ctypes.data_as(dp), ig[i].ctypes.data_as(dp), par[i].ctypes.data_as(dp),
+                      gl[i].ctypes.data_as(dp), act[i].ctypes.data_as(dp), 0, so.ctypes.data_as(dp), io.ctypes.data_as(dp),
+                      ob.ctypes.data_as(fp), rw.ctypes.data_as(dp), dn.ctypes.data_as(ip), nf.ctypes.data_as(ip), npj.ctypes.data_as(ip))
+            st[i], ig[i] = so, io
+            eplen[i] += 1
+            assert env.reward[i, 0] == rw[0] and bool(env.done[i, 0]) == bool(dn[0])
+            if dn[0] or eplen[i] >= limit:
+                assert np.array_equal(env.final_obs[i], ob)
+                episode[i] += 1; eplen[i] = 0; n_resets += 1
+                F.tw_reset(C.byref(ref_cfg), i, int(episode[i]), 0, st[i].ctypes.data_as(dp), ig[i].ctypes.data_as(dp),
+                           par[i].ctypes.data_as(dp), gl[i].ctypes.data_as(dp))
+                F.tw_norm_error_state(C.byref(ref_cfg), st[i].ctypes.data_as(dp), ig[i].ctypes.data_as(dp), gl[i].ctypes.data_as(dp),
+                                      ob.ctypes.data_as(fp))
+            assert np.array_equal(env.obs[i], ob), (t, i)
+        assert np.array_equal(env.state.T, st) and np.array_equal(env.integ.T, ig), t
+        assert np.array_equal(env.params.T, par) and np.array_equal(env.goal.T, gl), t
+    assert n_resets > n and env.stats[0] == n_resets and env.stats[7] == steps * n
+
+
+def test_kernel_inkernel_actions_and_sharding(libs):
+    """Philox actions drawn inside the kernel (single- and multi-step launches) and independence of the split into
+    handles: one 160-env handle against two 80-env shards with env_id_offset."""
+    K, F = libs
+    kw = dict(seed=21, autoreset=1, goal_mode=1, max_episode_steps=11)
+    whole = HostEnv(K, _config(1, n_envs=160, **kw), warps=2)
+    parts = [HostEnv(K, _config(1, n_envs=80, env_id_offset=80 * i, **kw), warps=3) for i in range(2)]
+    for e in [whole] + parts:
+        _reset_all(F, e.cfg, e)
+        e.launch(None, n_steps=15)
+        for _ in range(4):
+            e.launch(None)
+    for name in ("state", "integ", "params", "goal"):
+        assert np.array_equal(np.concatenate([getattr(p, name) for p in parts], axis=1), getattr(whole, name)), name
+    for name in ("obs", "reward", "done", "ep_length", "ep_index"):
+        assert np.array_equal(np.concatenate([getattr(p, name) for p in parts], axis=0), getattr(whole, name)), name
+    assert whole.stats[0] == sum(p.stats[0] for p in parts) >= 160 and whole.stats[7] == 19 * 160
