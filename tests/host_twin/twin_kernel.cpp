@@ -114,3 +114,29 @@ extern "C" int tw_kstep(const qr_config* cfg, const tw_arrays* b, int64_t env_lo
     }
     return 0;
 }
+
+// The per-thread companion kernels (no warp collectives): k_reset (0), k_init_goal (1), k_goal_update (2),
+// k_norm_error_state (3), run thread by thread over [env_lo, env_hi).
+extern "C" int tw_companion(const qr_config* cfg, const tw_arrays* b, int which, const uint8_t* mask, int env_type)
+{
+    fill_tables();
+    unsigned long long tile_counter[2] = {0, 0};
+    const int64_t env_lo = 0, env_hi = cfg->n_envs;
+    const int n_steps = 1;
+    blockDim.x = QR_BLOCK; gridDim.x = (unsigned)((cfg->n_envs + QR_BLOCK - 1) / QR_BLOCK);
+#define TW_COMPANION(T)                                                                            \
+    {                                                                                              \
+        TW_FILL(T)                                                                                 \
+        for (unsigned blk = 0; blk < gridDim.x; ++blk)                                             \
+            for (unsigned t = 0; t < (unsigned)QR_BLOCK; ++t) {                                    \
+                blockIdx.x = blk; threadIdx.x = t;                                                 \
+                if (which == 0) k_reset<T>(a, mask, env_type);                                     \
+                else if (which == 1) k_init_goal<T>(a, mask);                                      \
+                else if (which == 2) k_goal_update<T>(a);                                          \
+                else k_norm_error_state<T>(a, mask);                                               \
+            }                                                                                      \
+    }
+    if (cfg->dtype == QR_F64) TW_COMPANION(double) else TW_COMPANION(float)
+    blockIdx.x = 0; threadIdx.x = 0;
+    return 0;
+}

@@ -46,6 +46,7 @@ def libs(tmp_path_factory):
     tmp = str(tmp_path_factory.mktemp("twink"))
     K = _build("twin_kernel.cpp", tmp, "libtwink.so")
     K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int]
+    K.tw_companion.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int, C.c_void_p, C.c_int]
     F = _build("twin.cpp", tmp, "libtwin.so", "-O2")
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     F.tw_step.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, C.c_int, dp, dp, C.POINTER(C.c_float), dp, ip, ip, ip]
@@ -88,12 +89,23 @@ class HostEnv:
         self.state[:] = np.asarray(st).T; self.integ[:] = np.asarray(ig).T
         self.params[:] = np.asarray(par).T; self.goal[:] = np.asarray(goal).T
 
-    def launch(self, actions=None, n_steps=1, store=False):
+    def _arrays(self):
         b = TwArrays()
-        keep = []
         for name in ("state", "integ", "params", "goal", "traj", "obs", "reward", "done", "terminated", "truncated", "final_obs",
                      "nfev", "status", "ep_return", "ep_length", "ep_index", "stats"):
             setattr(b, name, getattr(self, name).ctypes.data)
+        return b
+
+    def companion(self, which, mask=None, env_type=0):
+        """k_reset / k_init_goal / k_goal_update / k_norm_error_state (qr_reset, qr_init_goal, qr_goal_update, ...)."""
+        b = self._arrays()
+        mp = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data
+        assert self.K.tw_companion(C.byref(self.cfg), C.byref(b), {"reset": 0, "init_goal": 1, "goal_update": 2,
+                                                                 "norm_error_state": 3}[which], mp, env_type) == 0
+
+    def launch(self, actions=None, n_steps=1, store=False):
+        b = self._arrays()
+        keep = []
         if actions is not None:
             actions = np.ascontiguousarray(actions)
             assert actions.dtype in (np.float32, np.float64) and actions.shape[-2:] == (self.n, self.A)
@@ -272,3 +284,67 @@ def test_kernel_inkernel_actions_and_sharding(libs):
     for name in ("obs", "reward", "done", "ep_length", "ep_index"):
         assert np.array_equal(np.concatenate([getattr(p, name) for p in parts], axis=0), getattr(whole, name)), name
     assert whole.stats[0] == sum(p.stats[0] for p in parts) >= 160 and whole.stats[7] == 19 * 160
+
+
+@pytest.mark.parametrize("name,gm", [("hover", 2), ("circle", 3), ("eight", 4), ("circle_manual", 3), ("takeoff", 5), ("land", 6),
+                                     ("land_low", 6), ("stay", 7)])
+def test_kernel_trajectory_modes_match_reference(libs, name, gm):
+    """test_gpu_parity.py::test_trajectory_modes_match_reference through the emulated k_init_goal / k_goal_update:
+    goal modes QR_GOAL_TRAJ_HOVER ... QR_GOAL_TRAJ_STAY call by call against the reference's TrajectoryGenerator."""
+    K, _ = libs
+    g = np.load(os.path.join(G, "traj_modes.npz"))
+    st, goal_ref, bdd_ref, t_ref = g[name + "_state"], g[name + "_goal"], g[name + "_b1d_dot"], g[name + "_t"]
+    t_traj, w, smooth, theta0 = g[name + "_draws"]
+    env = HostEnv(K, _config(1, n_envs=1, goal_mode=gm), warps=1)
+    par = np.array([[2.15, 0.23, 0.022, 0.035, 0.0135, 2.2]])
+    gl0 = np.zeros((1, 12)); gl0[0, 6] = 1.0
+    env.set_state(st[0:1], np.zeros((1, 8)), par, gl0)
+    env.companion("init_goal")                      # mark_traj_start + first get_desired on the float32 reset state
+    ts = env.traj
+    if name == "hover":                             # inject the reference run's two random draws
+        ts[8, 0] = t_traj; ts[7, 0] = smooth; ts[6, 0] = w
+    if name == "circle_manual":
+        ts[8, 0] = 1.75                             # the golden run shortened the circle to reach manual mode
+    if name != "hover":
+        assert np.abs(env.goal[:, 0] - goal_ref[0]).max() < 1e-11
+    worst = 0.0
+    for i in range(1, len(t_ref)):
+        env.state[:, 0] = st[i]
+        env.companion("goal_update")
+        worst = max(worst, np.abs(env.goal[:, 0] - goal_ref[i]).max(), np.abs(ts[9:11, 0] - bdd_ref[i, 0:2]).max())
+        assert abs(ts[0, 0] - t_ref[i]) < 1e-12
+    assert worst < 1e-11, worst
+    assert bool(int(ts[1, 0]) & 2) == bool(g[name + "_manual"][-1])
+
+
+def test_kernel_autoreset_equals_companion_kernels(libs):
+    """test_gpu_parity.py::test_autoreset_equals_manual_protocol on the emulator: auto reset inside k_step against
+    k_step -> k_reset(mask) -> k_init_goal(mask) -> k_norm_error_state(mask) (main.py:212-230)."""
+    K, _ = libs
+    n, limit = 70, 9
+    kw = dict(n_envs=n, seed=3, goal_mode=1)
+    a = HostEnv(K, _config(1, autoreset=1, max_episode_steps=limit, **kw), warps=2)
+    b = HostEnv(K, _config(1, autoreset=0, **kw), warps=2)
+    for e in (a, b):
+        e.companion("reset"); e.companion("init_goal"); e.companion("norm_error_state")
+    assert np.array_equal(a.state, b.state) and np.array_equal(a.obs, b.obs) and (a.ep_index == 1).all()
+    steps_b = np.zeros(n, np.int64)
+    rng = np.random.default_rng(9)
+    n_resets = 0
+    for t in range(28):
+        act = rng.uniform(-1, 1, (n, 4))
+        a.launch(act); b.launch(act)
+        steps_b += 1
+        assert np.array_equal(a.reward, b.reward) and np.array_equal(a.done, b.done)
+        need = b.done[:, 0].astype(bool) | (steps_b >= limit)
+        assert np.array_equal(a.terminated.astype(bool), b.done[:, 0].astype(bool)) and np.array_equal(a.truncated.astype(bool), steps_b >= limit)
+        if need.any():
+            term_obs = b.obs.copy()
+            b.companion("reset", mask=need); b.companion("init_goal", mask=need); b.companion("norm_error_state", mask=need)
+            steps_b[need] = 0
+            assert np.array_equal(a.final_obs[need], term_obs[need])
+            n_resets += int(need.sum())
+        assert np.array_equal(a.obs, b.obs), t
+        for name in ("state", "goal", "params", "integ"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), (t, name)
+    assert n_resets > n and a.stats[0] == n_resets
