@@ -192,7 +192,9 @@ def run_ours(args):
         actors = torch.empty((n, env.act_dim), dtype=torch.float32, device=dev)   # action buffer of qr_policy_td3
 
     def one_step(i):
-        if actors is not None:
+        if actors is not None and fused > 1:
+            env.rollout(fused, actions="policy")   # obs -> shipped actor -> env.step, `fused` times, in ONE launch
+        elif actors is not None:
             env.step(env.policy_td3(out=actors))   # compiled actor kernel + step kernel: two launches per env.step
         elif fused > 1:
             env.rollout(fused)      # `fused` env.step() calls in one launch, Philox actions drawn in-kernel

@@ -16,6 +16,7 @@ INT_DOP853, INT_EULER = 0, 1
 ENV_TRAIN, ENV_EVAL = 0, 1
 GOAL_EXTERNAL, GOAL_TRAJ_MODE0, GOAL_TRAJ_HOVER, GOAL_TRAJ_CIRCLE, GOAL_TRAJ_EIGHT = 0, 1, 2, 3, 4
 GOAL_TRAJ_TAKEOFF, GOAL_TRAJ_LAND, GOAL_TRAJ_STAY = 5, 6, 7
+ACT_POLICY = 2   # qr_rollout: actions from the shipped TD3 actor, evaluated inside the kernel
 ST_NONFINITE, ST_TOO_SMALL_STEP, ST_SVD = 1, 2, 4
 NUM_STATS = 16
 STAT_NAMES = ["episodes", "return0", "return1", "length", "crashed", "truncated", "return0_sq", "steps",

@@ -211,7 +211,10 @@ template <typename T> struct warp_smem {
 // GOAL1: the goal is generated on the device in trajectory mode 0 (config goal_mode == 1) -- a template parameter so
 // that this configuration has no global load at the end of a step (it would share a scoreboard with the loads that
 // fetch the next env, and wait for them).
-template <typename T, int MODE, bool MULTI, bool GOAL1>
+// POLICY: the action of every (sub-)step is the reference's shipped TD3 actor evaluated on the env's latest observation
+// (agent.choose_action(obs, explor_noise_std=0), algos/td3/td3.py:93-96; the evaluation loop of main.py:304-365 fused
+// into the launch).  Only instantiated for the wrapper modes with MULTI = true.
+template <typename T, int MODE, bool MULTI, bool GOAL1, bool POLICY = false>
 __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid_constant__ StepArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -386,8 +389,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 // full sectors; measured 5 % faster than a general coalescing copy through shared memory).  When the
                 // whole warp finishes 32 consecutive envs together (`coop`: the lock-step regime of a trained
                 // policy), the rows go through a shared tile and leave as 16-byte stores of one contiguous block.
-                obs1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : (last ? a.obs + e * O : nullptr);
-                obs2 = (a.obs_roll && last) ? a.obs + e * O : nullptr;
+                obs1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : ((last || POLICY) ? a.obs + e * O : nullptr);
+                obs2 = (a.obs_roll && (last || POLICY)) ? a.obs + e * O : nullptr;   // POLICY: the actor reads a.obs at the next sub-step
                 if (coop) {
                     float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
 #pragma unroll
@@ -433,8 +436,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 __syncwarp();
                 const float4* tile4 = reinterpret_cast<const float4*>(ks);
                 constexpr int NV = 32 * O / 4;   // float4 elements of the 32-row block
-                float4* g1 = reinterpret_cast<float4*>(a.obs_roll ? a.obs_roll + ((int64_t)k * N + e_first) * O : (last ? a.obs + e_first * O : nullptr));
-                float4* g2 = reinterpret_cast<float4*>((a.obs_roll && last) ? a.obs + e_first * O : nullptr);
+                float4* g1 = reinterpret_cast<float4*>(a.obs_roll ? a.obs_roll + ((int64_t)k * N + e_first) * O : ((last || POLICY) ? a.obs + e_first * O : nullptr));
+                float4* g2 = reinterpret_cast<float4*>((a.obs_roll && (last || POLICY)) ? a.obs + e_first * O : nullptr);
 #pragma unroll
                 for (int it = 0; it < (NV + 31) / 32; ++it) {
                     const int q = it * 32 + lane;
@@ -672,7 +675,18 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 #pragma unroll
                 for (int i = 0; i < 12; ++i) prefetch_l2(a.goal + i * N + e);
             }
-            if (!a.actions) {
+            if (POLICY) {
+                // obs -> action with the compiled actor(s); the row was written by this env's previous step (by this
+                // thread, or by its warp through the shared tile / by an earlier launch)
+                float xo[23], af[5];
+#pragma unroll
+                for (int i = 0; i < O; ++i) xo[i] = a.obs[e * O + i];
+                if (MODE == 1) actor_td3_mono(xo, af);
+                else { actor_td3_modul1(xo, af); actor_td3_modul2(xo + 15, af + 4); }
+#pragma unroll
+                for (int i = 0; i < A; ++i) act[i] = (T)af[i];
+                act_f32 = true;   // the torch actor returns float32 actions (numpy then computes the thrust in float32)
+            } else if (!a.actions) {
                 const uint64_t gid = (uint64_t)(a.env_id_offset + e);
                 uint32_t rnd[8];
                 cp_async_wait_all();

@@ -51,7 +51,7 @@ struct qr_handle {
     double* d_stage; size_t d_stage_bytes;
     cudaStream_t io_stream;
     unsigned long long* tile_counter;
-    int num_sms; int smem_optin; int attr_set[8];
+    int num_sms; int smem_optin; int attr_set[16];
 };
 
 namespace {
@@ -93,7 +93,8 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     if (hi <= lo) return QR_OK;
     qr::StepArgs<T> a = make_args<T>(h);
     a.env_lo = lo; a.env_hi = hi;
-    a.actions = actions; a.act_f32 = (act_dtype == QR_F32); a.n_steps = n_steps;
+    const bool policy = act_dtype == QR_ACT_POLICY;   // actions from the shipped actor, evaluated inside the kernel
+    a.actions = policy ? nullptr : actions; a.act_f32 = (act_dtype == QR_F32); a.n_steps = n_steps;
     a.obs_roll = obs_roll; a.reward_roll = (T*)reward_roll; a.done_roll = done_roll;
     // launches on different streams (qr_step_host pipelines two) must not share a tile counter
     a.tile_counter = h->tile_counter + ((s == h->io_stream) ? 1 : 0);
@@ -110,10 +111,14 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     const size_t smem = per_warp * warps;
     // single-step launches queue the envs whose episode ended and reset them in a second kernel; multi-step
     // launches (the env keeps stepping in its lane) reset inside the step kernel
-    const bool multi = n_steps > 1;
+    const bool multi = n_steps > 1 || policy;   // the policy variants exist for the in-kernel reset flavour only
     const bool goal1 = h->cfg.goal_mode == QR_GOAL_TRAJ_MODE0;   // only with a wrapper mode (checked in qr_create)
     void (*kern)(const qr::StepArgs<T>);
-    if (h->cfg.mode == QR_MODE_COUPLED)
+    if (policy && h->cfg.mode == QR_MODE_COUPLED)
+        kern = goal1 ? qr::k_step<T, 1, true, true, true> : qr::k_step<T, 1, true, false, true>;
+    else if (policy && h->cfg.mode == QR_MODE_DECOUPLED)
+        kern = goal1 ? qr::k_step<T, 2, true, true, true> : qr::k_step<T, 2, true, false, true>;
+    else if (h->cfg.mode == QR_MODE_COUPLED)
         kern = multi ? (goal1 ? qr::k_step<T, 1, true, true> : qr::k_step<T, 1, true, false>)
                      : (goal1 ? qr::k_step<T, 1, false, true> : qr::k_step<T, 1, false, false>);
     else if (h->cfg.mode == QR_MODE_DECOUPLED)
@@ -121,7 +126,7 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
                      : (goal1 ? qr::k_step<T, 2, false, true> : qr::k_step<T, 2, false, false>);
     else
         kern = multi ? qr::k_step<T, 0, true, false> : qr::k_step<T, 0, false, false>;
-    const int attr_idx = (sizeof(T) == 8 ? 4 : 0) + (multi ? 2 : 0) + (goal1 ? 1 : 0);
+    const int attr_idx = (policy ? 8 : 0) + (sizeof(T) == 8 ? 4 : 0) + (multi ? 2 : 0) + (goal1 ? 1 : 0);
     if (!h->attr_set[attr_idx]) {
         QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->smem_optin / per_warp * per_warp)));
         h->attr_set[attr_idx] = 1;
@@ -374,7 +379,10 @@ int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, fl
     if (n_steps <= 0) return fail(QR_ERR_INVALID, "qr_rollout: n_steps must be positive");
     if (n_steps > 1 && h->cfg.goal_mode >= QR_GOAL_TRAJ_HOVER)
         return fail(QR_ERR_INVALID, "qr_rollout: trajectory modes hover/circle/eight need qr_goal_update before every step (n_steps must be 1)");
-    if (actions && act_dtype != QR_F32 && act_dtype != QR_F64) return fail(QR_ERR_INVALID, "qr_rollout: bad act_dtype");
+    if (act_dtype == QR_ACT_POLICY) {
+        if (actions) return fail(QR_ERR_INVALID, "qr_rollout: act_dtype QR_ACT_POLICY takes no action array");
+        if (h->cfg.mode == QR_MODE_QUAD) return fail(QR_ERR_INVALID, "qr_rollout: the shipped actors exist for the wrapper modes only");
+    } else if (actions && act_dtype != QR_F32 && act_dtype != QR_F64) return fail(QR_ERR_INVALID, "qr_rollout: bad act_dtype");
     cudaStream_t s = (cudaStream_t)stream;
     if (h->cfg.dtype == QR_F64) return launch_step<double>(h, 0, h->cfg.n_envs, actions, act_dtype, n_steps, obs_out, reward_out, done_out, s);
     return launch_step<float>(h, 0, h->cfg.n_envs, actions, act_dtype, n_steps, obs_out, reward_out, done_out, s);

@@ -182,10 +182,16 @@ class BatchedQuadEnv:
     def rollout(self, n_steps, actions=None, store=False):
         """n_steps fused env.step() calls in ONE kernel launch (state stays in registers).
 
-        actions: [n_steps,N,A] tensor, or None for in-kernel Philox U(-1,1) actions.
+        actions: [n_steps,N,A] tensor, None for in-kernel Philox U(-1,1) actions, or "policy": the reference's
+        shipped TD3 actor evaluated inside the kernel on each env's latest observation (the evaluation loop
+        obs -> choose_action -> step of main.py:304-365 in one launch; self.obs must be current).
         store=True returns per-step (obs, reward, done) tensors [n_steps,N,..]."""
         ap, ad = None, nat.F32
-        if actions is not None:
+        if isinstance(actions, str):
+            if actions != "policy":
+                raise ValueError("actions must be a tensor, None or 'policy'")
+            ad = nat.ACT_POLICY
+        elif actions is not None:
             actions = actions.to(self.device).contiguous()
             assert tuple(actions.shape) == (n_steps, self.num_envs, self.act_dim)
             ap = C.c_void_p(actions.data_ptr()); ad = nat.F64 if actions.dtype == torch.float64 else nat.F32

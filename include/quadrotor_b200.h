@@ -38,6 +38,8 @@ extern "C" {
 enum { QR_OK = 0, QR_ERR_INVALID = 1, QR_ERR_CUDA = 2, QR_ERR_NOMEM = 3, QR_ERR_NO_DEVICE = 4 };
 enum { QR_MODE_QUAD = 0, QR_MODE_COUPLED = 1, QR_MODE_DECOUPLED = 2 };   /* Quad-v0 | CoupledWrapper | DecoupledWrapper */
 enum { QR_F32 = 0, QR_F64 = 1 };
+/* act_dtype of qr_rollout only: no action array, the reference's shipped TD3 actor is evaluated inside the kernel */
+enum { QR_ACT_POLICY = 2 };
 enum { QR_INT_DOP853 = 0, QR_INT_EULER = 1 };                            /* quad.py:62 */
 enum { QR_ENV_TRAIN = 0, QR_ENV_EVAL = 1 };                              /* reset(env_type=...) quad.py:171 */
 /* set_goal_state | on-device trajectory_generator: mode 0 (idle, evaluated inside qr_step), 1 hover, 5 circle, 6 figure
@@ -136,8 +138,11 @@ int qr_policy_td3(qr_handle* h, float* actions, void* stream);
 
 /* `n_steps` consecutive env.step() calls fused in one launch, state resident in registers.
  * actions: device [n_steps][N][A] or NULL = U(-1,1) actions drawn in-kernel with Philox (the synthetic
- * random-action workload).  obs_out/reward_out/done_out: device [n_steps][N][..] or NULL to keep only the
- * last step's outputs in the qr_buffers views. */
+ * random-action workload).  act_dtype = QR_ACT_POLICY (actions = NULL): every step's action is the shipped TD3 actor
+ * (as qr_policy_td3) evaluated in the kernel on the env's latest observation -- the evaluation loop of
+ * main.py:304-365 (obs -> agent.choose_action -> env.step) in one launch; the observation buffer must hold the
+ * current observations (qr_norm_error_state after a reset).  obs_out/reward_out/done_out: device
+ * [n_steps][N][..] or NULL to keep only the last step's outputs in the qr_buffers views. */
 int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, float* obs_out, void* reward_out,
                uint8_t* done_out, void* stream);
 

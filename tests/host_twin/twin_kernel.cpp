@@ -65,7 +65,7 @@ void fill_tables()   // as qr_create does for the device
     g_tab_done = true;
 }
 
-template <typename T, int MODE, bool MULTI, bool GOAL1> void lane_body(void* p) { k_step<T, MODE, MULTI, GOAL1>(*(const StepArgs<T>*)p); }
+template <typename T, int MODE, bool MULTI, bool GOAL1, bool POLICY = false> void lane_body(void* p) { k_step<T, MODE, MULTI, GOAL1, POLICY>(*(const StepArgs<T>*)p); }
 
 }  // namespace
 
@@ -78,11 +78,12 @@ struct tw_arrays {
     float* obs_roll; void* reward_roll; uint8_t* done_roll;
 };
 
-extern "C" int tw_kstep(const qr_config* cfg, const tw_arrays* b, int64_t env_lo, int64_t env_hi, int n_steps, int warps)
+extern "C" int tw_kstep(const qr_config* cfg, const tw_arrays* b, int64_t env_lo, int64_t env_hi, int n_steps, int warps, int policy)
 {
     fill_tables();
     unsigned long long tile_counter[2] = {0, 0};
-    const bool multi = n_steps > 1, goal1 = cfg->goal_mode == QR_GOAL_TRAJ_MODE0;
+    const bool multi = n_steps > 1 || policy, goal1 = cfg->goal_mode == QR_GOAL_TRAJ_MODE0;   // as launch_step()
+    if (policy && cfg->mode == QR_MODE_QUAD) return -2;
     if (warps < 1 || warps > 12) return -1;
     blockDim.x = (unsigned)warps * 32; gridDim.x = 1; blockIdx.x = 0;
 #define TW_FILL(T)                                                                                                            \
@@ -97,7 +98,8 @@ extern "C" int tw_kstep(const qr_config* cfg, const tw_arrays* b, int64_t env_lo
     a.obs_roll = b->obs_roll; a.reward_roll = (T*)b->reward_roll; a.done_roll = b->done_roll;
 #define TW_RUN(T, MODE)                                                                                                       \
     {                                                                                                                         \
-        void (*body)(void*) = multi ? (goal1 ? lane_body<T, MODE, true, true> : lane_body<T, MODE, true, false>)              \
+        void (*body)(void*) = policy ? (goal1 ? lane_body<T, MODE, true, true, true> : lane_body<T, MODE, true, false, true>)   \
+                            : multi ? (goal1 ? lane_body<T, MODE, true, true> : lane_body<T, MODE, true, false>)             \
                                     : (goal1 ? lane_body<T, MODE, false, true> : lane_body<T, MODE, false, false>);           \
         for (int w = 0; w < warps; ++w) simt::run_warp(body, &a, (unsigned)w * 32);                                           \
     }
@@ -139,4 +141,11 @@ extern "C" int tw_companion(const qr_config* cfg, const tw_arrays* b, int which,
     if (cfg->dtype == QR_F64) TW_COMPANION(double) else TW_COMPANION(float)
     blockIdx.x = 0; threadIdx.x = 0;
     return 0;
+}
+
+// the compiled actors on one observation row (what k_actor_td3 computes per env): mode 1 -> 4 actions, mode 2 -> 5
+extern "C" void tw_actor(int mode, const float* obs, float* act)
+{
+    if (mode == 1) actor_td3_mono(obs, act);
+    else { actor_td3_modul1(obs, act); actor_td3_modul2(obs + 15, act + 4); }
 }

@@ -45,7 +45,8 @@ def _build(src, tmp, name, opt="-O1"):
 def libs(tmp_path_factory):
     tmp = str(tmp_path_factory.mktemp("twink"))
     K = _build("twin_kernel.cpp", tmp, "libtwink.so")
-    K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int]
+    K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
+    K.tw_actor.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     K.tw_companion.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int, C.c_void_p, C.c_int]
     F = _build("twin.cpp", tmp, "libtwin.so", "-O2")
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -106,7 +107,8 @@ class HostEnv:
     def launch(self, actions=None, n_steps=1, store=False):
         b = self._arrays()
         keep = []
-        if actions is not None:
+        policy = isinstance(actions, str) and actions == "policy"
+        if actions is not None and not policy:
             actions = np.ascontiguousarray(actions)
             assert actions.dtype in (np.float32, np.float64) and actions.shape[-2:] == (self.n, self.A)
             keep.append(actions)
@@ -116,7 +118,7 @@ class HostEnv:
             out = (np.zeros((n_steps, self.n, self.O), np.float32), np.zeros((n_steps, self.n, self.G), self.T),
                    np.zeros((n_steps, self.n, self.G), np.uint8))
             b.obs_roll, b.reward_roll, b.done_roll = (x.ctypes.data for x in out)
-        rc = self.K.tw_kstep(C.byref(self.cfg), C.byref(b), 0, self.n, int(n_steps), self.warps)
+        rc = self.K.tw_kstep(C.byref(self.cfg), C.byref(b), 0, self.n, int(n_steps), self.warps, int(policy))
         assert rc == 0
         return out
 
@@ -348,3 +350,43 @@ def test_kernel_autoreset_equals_companion_kernels(libs):
         for name in ("state", "goal", "params", "integ"):
             assert np.array_equal(getattr(a, name), getattr(b, name)), (t, name)
     assert n_resets > n and a.stats[0] == n_resets
+
+
+@pytest.mark.parametrize("fw,tag", [("MONO", "mono"), ("MODUL", "modul")])
+def test_kernel_fused_policy_rollout_flies_the_reference_eval_episode(libs, fw, tag):
+    """qr_rollout(act_dtype = QR_ACT_POLICY): obs -> shipped TD3 actor -> env.step fused in the kernel, against the
+    evaluation episode the reference flew with the same checkpoint (tests/golden/eval_*.npz, KAT-2), and bit for bit
+    against stepping with the same actor applied outside the kernel."""
+    K, _ = libs
+    ep = np.load(os.path.join(G, "eval_%s.npz" % tag))
+    H = len(ep["reward"])
+    mode = 1 if fw == "MONO" else 2
+    n = 3
+    def fresh():
+        env = HostEnv(K, _config(mode, n_envs=n, goal_mode=1), warps=1)
+        env.set_state(np.tile(ep["state0"], (n, 1)), np.tile(ep["integ0"], (n, 1)), np.tile(ep["params"], (n, 1)),
+                      np.tile(ep["goal0"], (n, 1)))
+        env.obs[:] = np.tile(ep["obs0"], (n, 1))
+        return env
+    fused = fresh()
+    obs_r, rew_r, done_r = fused.launch("policy", n_steps=H, store=True)
+    assert not done_r.any()
+    assert np.abs(fused.state.T[0] - ep["state"][-1]).max() < 1e-3
+    ret = rew_r[:, 0, :].sum(axis=0)
+    assert np.abs(ret - ep["reward"].sum(axis=0)).max() < 0.05 and ret[0] > 985
+    assert np.abs(fused.state.T - fused.state.T[0]).max() == 0.0          # identical envs stay identical
+    # the same loop with the actor outside the kernel (first 60 steps): identical bits
+    loop = fresh()
+    act = np.empty((n, loop.A), np.float32)
+    fp = C.POINTER(C.c_float)
+    for t in range(60):
+        for i in range(n):
+            K.tw_actor(mode, loop.obs[i].ctypes.data_as(fp), act[i].ctypes.data_as(fp))
+        loop.launch(act)
+        assert np.array_equal(loop.obs, obs_r[t]) and np.array_equal(loop.reward, rew_r[t]), t
+    # single-step policy launches continue a fused rollout seamlessly
+    a2, b2 = fresh(), fresh()
+    a2.launch("policy", n_steps=7)
+    for _ in range(7):
+        b2.launch("policy", n_steps=1)
+    assert np.array_equal(a2.state, b2.state) and np.array_equal(a2.obs, b2.obs) and np.array_equal(a2.integ, b2.integ)

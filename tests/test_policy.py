@@ -99,6 +99,36 @@ def test_compiled_actor_in_the_loop_flies_the_reference_episode():
     env.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("fw,tag", [("MONO", "mono"), ("MODUL", "modul")])
+def test_fused_policy_rollout_flies_the_reference_episode(fw, tag):
+    """qr_rollout(act_dtype = QR_ACT_POLICY): the evaluation loop obs -> shipped actor -> env.step of main.py:304-365
+    in ONE launch, 1000 steps, against the episode the reference flew (KAT-2); bit-identical to the two-kernel loop
+    (qr_policy_td3 + qr_step).  The same test runs on the CPU emulator in tests/test_host_twin_kernel.py."""
+    from gym_rotor_b200 import vec_env
+    ep = np.load(os.path.join(G, "eval_%s.npz" % tag))
+    H, n = len(ep["reward"]), 64
+
+    def fresh():
+        env = vec_env.BatchedQuadEnv(n, framework=fw, dtype=torch.float64, goal_mode="traj0")
+        env.set_state(np.tile(ep["state0"], (n, 1)), np.tile(ep["integ0"], (n, 1)), np.tile(ep["params"], (n, 1)),
+                      np.tile(ep["goal0"], (n, 1)))
+        env.obs.copy_(torch.as_tensor(np.tile(ep["obs0"], (n, 1)), device="cuda:0"))
+        return env
+    fused = fresh()
+    obs_r, rew_r, done_r = fused.rollout(H, actions="policy", store=True)
+    assert not bool(done_r.any())
+    st = fused.get_state()[0]
+    assert np.abs(st[0] - ep["state"][-1]).max() < 1e-3 and np.abs(st - st[0]).max() == 0.0
+    ret = rew_r[:, 0, :].sum(dim=0).cpu().numpy()
+    assert np.abs(ret - ep["reward"].sum(axis=0)).max() < 0.05 and ret[0] > 985
+    loop = fresh()
+    for t in range(50):
+        o_n, rew, done, _, _ = loop.step(loop.policy_td3())
+        assert torch.equal(torch.cat(o_n, dim=1), obs_r[t]) and torch.equal(rew, rew_r[t]), t
+    fused.close(); loop.close()
+
+
 def test_trainer_side_helpers_match_reference_formulas():
     """benchmark_reward (utils/utils.py:42-47 on get_error_state, :21-39) and the time-limit relabel (main.py:169-173)."""
     from gym_rotor_b200.vec_env import benchmark_reward, time_limit_relabel
