@@ -14,6 +14,11 @@
 #include "qr_traj.cuh"
 #include "generated/actor_td3.cuh"
 
+// experimental (off: not measured yet): claim the next 32-env tile one acquisition ahead, so that the L2 round trip
+// of the tile counter's atomic (2.9 % of the stall samples in capture r01u) overlaps a whole round of work
+#ifndef QR_TILE_PREFETCH
+#define QR_TILE_PREFETCH 0
+#endif
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
@@ -243,6 +248,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     int64_t tile_base = 0;    // warp-uniform: first env of the tile currently being handed out
     int tile_pos = 32;        // warp-uniform: envs of that tile already taken (32 = none left)
     bool exhausted = false;   // warp-uniform: the counter ran past the last tile
+#if QR_TILE_PREFETCH
+    unsigned long long pend = ~0ULL;   // lane 0: tile claimed ahead of need (~0 = none)
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+#endif
 
     // per-lane persistent state (registers).  Everything that is only needed when a step ENDS -- integral
     // errors, the goal of the step in flight, episode return / length / index -- lives in the lane's stash in
@@ -285,7 +294,16 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 int64_t base2 = -1;
                 if (cnt > rem && !exhausted) {
                     unsigned long long t = 0;
+#if QR_TILE_PREFETCH
+                    if (lane == 0) {
+                        t = (pend != ~0ULL) ? pend : atomicAdd(a.tile_counter, 1ULL);
+                        // not in the last wave of the launch: a claimed tile is bound to this warp, which would
+                        // lengthen the tail of the persistent grid
+                        pend = (t + total_warps < (unsigned long long)ntiles) ? atomicAdd(a.tile_counter, 1ULL) : ~0ULL;
+                    }
+#else
                     if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
+#endif
                     t = __shfl_sync(FULL, t, 0);
                     if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
                     else exhausted = true;
@@ -577,6 +595,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 QR_PKI(50) = (int32_t)(uint32_t)e_next; QR_PKI(51) = (int32_t)(e_next >> 32);
                 QR_PKI(52) = (int32_t)(uint32_t)tile_base; QR_PKI(53) = (int32_t)(tile_base >> 32);
                 QR_PKI(54) = tile_pos; QR_PKI(55) = rq_n;
+#if QR_TILE_PREFETCH
+                QR_PKI(56) = (int32_t)(uint32_t)pend; QR_PKI(57) = (int32_t)(pend >> 32);
+#endif
                 if (do_reset) {
                     float dummy[23];
                     // the new episode's first observation replaces the terminal one in the step's output row
@@ -599,6 +620,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 e_next = (int64_t)(((uint64_t)(uint32_t)QR_PKI(51) << 32) | (uint32_t)QR_PKI(50));
                 tile_base = (int64_t)(((uint64_t)(uint32_t)QR_PKI(53) << 32) | (uint32_t)QR_PKI(52));
                 tile_pos = QR_PKI(54); rq_n = QR_PKI(55);
+#if QR_TILE_PREFETCH
+                pend = ((unsigned long long)(uint32_t)QR_PKI(57) << 32) | (uint32_t)QR_PKI(56);
+#endif
 #undef QR_PKI
                 if (do_reset) {
                     const T* sc = ks + lane * 32;   // what auto_reset_env left in this lane's scratch

@@ -32,9 +32,9 @@ class TwArrays(C.Structure):
                [(n, C.c_void_p) for n in ("obs_roll", "reward_roll", "done_roll")]
 
 
-def _build(src, tmp, name, opt="-O1"):
+def _build(src, tmp, name, opt="-O1", defines=()):
     out = os.path.join(tmp, name)
-    cmd = ["g++", "-std=c++17", opt, "-ffp-contract=off", "-fPIC", "-shared", "-I" + CUDA_INC, "-I" + TWIN_DIR,
+    cmd = ["g++", "-std=c++17", opt, "-ffp-contract=off", "-fPIC", "-shared"] + ["-D" + d for d in defines] + ["-I" + CUDA_INC, "-I" + TWIN_DIR,
            "-I" + os.path.join(ROOT, "gym_rotor_b200", "csrc"), "-o", out, os.path.join(TWIN_DIR, src)]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
@@ -390,3 +390,24 @@ def test_kernel_fused_policy_rollout_flies_the_reference_eval_episode(libs, fw, 
     for _ in range(7):
         b2.launch("policy", n_steps=1)
     assert np.array_equal(a2.state, b2.state) and np.array_equal(a2.obs, b2.obs) and np.array_equal(a2.integ, b2.integ)
+
+
+def test_kernel_experimental_tile_prefetch_is_equivalent(tmp_path):
+    """QR_TILE_PREFETCH (compile-time experiment, off in the product build): claiming the next tile one acquisition
+    ahead must not lose, duplicate or reorder work -- same outputs as the default build on a many-tile launch."""
+    outs = []
+    for defs in ((), ("QR_TILE_PREFETCH=1",)):
+        K = _build("twin_kernel.cpp", str(tmp_path), "libtwink_%d.so" % len(defs), defines=defs)
+        K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
+        g = np.load(os.path.join(G, "step_mono_a64.npz"))
+        n = g["action"].shape[0]
+        env = HostEnv(K, _config(1, n_envs=n, autoreset=1, max_episode_steps=3), warps=4)
+        env.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
+        env.ep_index[:] = 1
+        rng = np.random.default_rng(1)
+        for t in range(4):
+            env.launch(rng.uniform(-1, 1, (n, 4)))
+        outs.append((env.state.copy(), env.obs.copy(), env.ep_index.copy(), env.stats.copy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert outs[0][3][7] == 4 * 1200 and outs[0][3][0] >= 1200
