@@ -392,13 +392,16 @@ def test_kernel_fused_policy_rollout_flies_the_reference_eval_episode(libs, fw, 
     assert np.array_equal(a2.state, b2.state) and np.array_equal(a2.obs, b2.obs) and np.array_equal(a2.integ, b2.integ)
 
 
-def test_kernel_experimental_tile_prefetch_is_equivalent(tmp_path):
+def test_kernel_experimental_tile_prefetch_is_equivalent(libs, tmp_path):
     """QR_TILE_PREFETCH (compile-time experiment, off in the product build): claiming the next tile one acquisition
     ahead must not lose, duplicate or reorder work -- same outputs as the default build on a many-tile launch."""
     outs = []
     for defs in ((), ("QR_TILE_PREFETCH=1",)):
-        K = _build("twin_kernel.cpp", str(tmp_path), "libtwink_%d.so" % len(defs), defines=defs)
-        K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
+        if defs:
+            K = _build("twin_kernel.cpp", str(tmp_path), "libtwink_pre.so", defines=defs)
+            K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
+        else:
+            K = libs[0]
         g = np.load(os.path.join(G, "step_mono_a64.npz"))
         n = g["action"].shape[0]
         env = HostEnv(K, _config(1, n_envs=n, autoreset=1, max_episode_steps=3), warps=4)
