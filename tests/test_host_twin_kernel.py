@@ -384,6 +384,13 @@ def test_kernel_fused_policy_rollout_flies_the_reference_eval_episode(libs, fw, 
             K.tw_actor(mode, loop.obs[i].ctypes.data_as(fp), act[i].ctypes.data_as(fp))
         loop.launch(act)
         assert np.array_equal(loop.obs, obs_r[t]) and np.array_equal(loop.reward, rew_r[t]), t
+    # a full warp in lock step (the coalesced observation path feeds the actor) agrees with the 3-env run
+    full = HostEnv(K, _config(mode, n_envs=32, goal_mode=1), warps=1)
+    full.set_state(np.tile(ep["state0"], (32, 1)), np.tile(ep["integ0"], (32, 1)), np.tile(ep["params"], (32, 1)),
+                   np.tile(ep["goal0"], (32, 1)))
+    full.obs[:] = np.tile(ep["obs0"], (32, 1))
+    obs_f, rew_f, _ = full.launch("policy", n_steps=120, store=True)
+    assert np.array_equal(obs_f[:, :3], obs_r[:120]) and np.array_equal(obs_f[:, 31], obs_r[:120, 0])
     # single-step policy launches continue a fused rollout seamlessly
     a2, b2 = fresh(), fresh()
     a2.launch("policy", n_steps=7)
