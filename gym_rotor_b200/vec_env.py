@@ -28,6 +28,44 @@ def _view(ptr, shape, typestr, device):
     return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
 
 
+class Box:
+    """Stand-in for gymnasium.spaces.Box with what the reference's callers use (quad.py:120-132; utils/utils.py:17-18
+    seeds both spaces): low / high / shape / dtype, seed(), sample(), contains().  gymnasium is not a dependency."""
+
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        if shape is None:
+            shape = np.shape(low)
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.low = np.broadcast_to(np.asarray(low, self.dtype), self.shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, self.dtype), self.shape).copy()
+        self._rng = np.random.default_rng()
+
+    def seed(self, seed=None):
+        self._rng = np.random.default_rng(seed)
+        return [seed]
+
+    def sample(self):
+        return self._rng.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+
+def forces_to_fM_matrices(d, c_tf):
+    """forces_to_fM of quad.py:396-401 for per-env arm lengths d [N] and torque coefficients c_tf [N] -> [N,4,4]
+    (rows f, M1, M2, M3; columns T1..T4), and its inverse fM_to_forces (quad.py:402)."""
+    d = torch.as_tensor(d, dtype=torch.float64).reshape(-1)
+    c = torch.as_tensor(c_tf, dtype=torch.float64, device=d.device).reshape(-1)
+    one, zero = torch.ones_like(d), torch.zeros_like(d)
+    A = torch.stack([torch.stack([one, one, one, one], dim=1),
+                     torch.stack([zero, -d, zero, d], dim=1),
+                     torch.stack([d, zero, -d, zero], dim=1),
+                     torch.stack([-c, c, -c, c], dim=1)], dim=1)
+    return A, torch.linalg.inv(A)
+
+
 class BatchedQuadEnv:
     """N quadrotor envs on one GPU.  `framework`: 'MONO' (CoupledWrapper), 'MODUL' (DecoupledWrapper), 'QUAD' (Quad-v0)."""
 
@@ -90,8 +128,24 @@ class BatchedQuadEnv:
         self.eIx_lim, self.eIb1_lim = cfg.eIx_lim, cfg.eIb1_lim
         self.min_force = cfg.min_force
         self.alpha, self.beta = cfg.alpha, cfg.beta
+        # spaces as the reference declares them (quad.py:104-132): raw-state bounds, normalised actions
+        hi = np.concatenate([cfg.x_lim * np.ones(3), cfg.v_lim * np.ones(3), np.ones(9), cfg.W_lim * np.ones(3)]).astype(np.float32)
+        self.observation_space = Box(-hi, hi, dtype=np.float32)
+        self.action_space = Box(-1.0, 1.0, shape=(self.act_dim,), dtype=np.float32)
 
     # ---- reference attribute surface (per-env where domain randomisation makes them per-env) ----
+    J_nominal = np.diag([0.022, 0.022, 0.035])   # quad.py:30
+
+    @property
+    def forces_to_fM(self):
+        """[N,4,4] float64: quad.py:396-401 with each env's (randomised) arm length and torque coefficient."""
+        return forces_to_fM_matrices(self.params_soa[1], self.params_soa[4])[0]
+
+    @property
+    def fM_to_forces(self):
+        """[N,4,4] float64: inverse of forces_to_fM (quad.py:402; read by draw_plot.py:63,70)."""
+        return forces_to_fM_matrices(self.params_soa[1], self.params_soa[4])[1]
+
     @property
     def hover_force(self):
         return self.params_soa[0] * self.g / 4.0

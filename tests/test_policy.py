@@ -129,6 +129,37 @@ def test_fused_policy_rollout_flies_the_reference_episode(fw, tag):
     fused.close(); loop.close()
 
 
+@pytest.mark.gpu
+def test_reference_attribute_surface_on_device():
+    """What the reference's callers read off the env object: spaces, limits, force constants, matrices."""
+    from gym_rotor_b200 import vec_env
+    env = vec_env.BatchedQuadEnv(8, framework="MODUL", dtype=torch.float32)
+    env.reset()
+    assert env.action_space.shape == (5,) and env.observation_space.shape == (18,)
+    env.action_space.seed(1); env.observation_space.seed(1)          # utils/utils.py:17-18
+    assert (env.x_lim, env.v_lim, env.eIx_lim, env.eIb1_lim, env.dt) == (1.0, 4.0, 3.0, 3.0, 1.0 / 200)
+    m, c_tw = env.params_soa[0], env.params_soa[5]
+    assert torch.allclose(env.hover_force, m * 9.81 / 4) and torch.allclose(env.max_force, c_tw * env.hover_force)
+    assert torch.allclose(env.scale_act + env.avrg_act, env.max_force)
+    A, Ainv = env.forces_to_fM, env.fM_to_forces
+    assert A.shape == (8, 4, 4) and float((A @ Ainv - torch.eye(4, dtype=torch.float64, device=A.device)).abs().max()) < 1e-12
+    assert env.J_nominal.shape == (3, 3)
+    env.close()
+
+
+def test_reference_attribute_surface_without_gymnasium():
+    """Box stand-in (set_seed seeds both spaces, utils/utils.py:17-18) and forces_to_fM / fM_to_forces (quad.py:396-402)."""
+    from gym_rotor_b200.vec_env import Box, forces_to_fM_matrices
+    sp = Box(-1.0, 1.0, shape=(4,), dtype=np.float32)
+    sp.seed(7); a = sp.sample(); sp.seed(7); b = sp.sample()
+    assert a.dtype == np.float32 and a.shape == (4,) and np.array_equal(a, b) and sp.contains(a) and not sp.contains(a + 3)
+    d, c = np.array([0.23, 0.25]), np.array([0.0135, 0.012])
+    A, Ainv = forces_to_fM_matrices(d, c)
+    for i in range(2):
+        ref = np.array([[1.0, 1.0, 1.0, 1.0], [0.0, -d[i], 0.0, d[i]], [d[i], 0.0, -d[i], 0.0], [-c[i], c[i], -c[i], c[i]]])
+        assert np.array_equal(A[i].numpy(), ref) and np.abs(Ainv[i].numpy() - np.linalg.inv(ref)).max() < 1e-12
+
+
 def test_trainer_side_helpers_match_reference_formulas():
     """benchmark_reward (utils/utils.py:42-47 on get_error_state, :21-39) and the time-limit relabel (main.py:169-173)."""
     from gym_rotor_b200.vec_env import benchmark_reward, time_limit_relabel
