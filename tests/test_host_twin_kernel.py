@@ -209,8 +209,8 @@ def _reset_all(F, cfg, env, episode=1):
     return st, ig, par, gl
 
 
-@pytest.mark.parametrize("dtype64", [True, False])
-def test_kernel_rollout_with_autoreset_equals_single_steps(libs, dtype64):
+@pytest.mark.parametrize("dtype64,act64", [(True, True), (False, False), (False, True), (True, False)])
+def test_kernel_rollout_with_autoreset_equals_single_steps(libs, dtype64, act64):
     """Multi-step launch (reset at the parked call site, env stays in its lane) == single-step launches (queued resets,
     batches of >= 24 and bursts of a common time limit), ragged n, misaligned rollout rows."""
     K, F = libs
@@ -220,7 +220,7 @@ def test_kernel_rollout_with_autoreset_equals_single_steps(libs, dtype64):
     e1, e2 = HostEnv(K, c1, warps=2), HostEnv(K, c2, warps=5)
     _reset_all(F, c1, e1); _reset_all(F, c2, e2)
     rng = np.random.default_rng(15)
-    acts = rng.uniform(-1, 1, (steps, n, 4)).astype(np.float64 if dtype64 else np.float32)
+    acts = rng.uniform(-1, 1, (steps, n, 4)).astype(np.float64 if act64 else np.float32)   # staged or loaded at the step start
     obs_r, rew_r, done_r = e1.launch(acts, n_steps=steps, store=True)
     for k in range(steps):
         e2.launch(acts[k])
@@ -421,3 +421,24 @@ def test_kernel_experimental_tile_prefetch_is_equivalent(libs, tmp_path):
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
     assert outs[0][3][7] == 4 * 1200 and outs[0][3][0] >= 1200
+
+
+def test_kernel_modul_quad_rollouts_and_external_goals(libs):
+    """DecoupledWrapper and Quad-v0 through multi-step launches with EXTERNAL goals (the goal is read from the goal
+    buffer at the end of every step) == single-step launches; float32; auto reset off and on."""
+    K, F = libs
+    rng = np.random.default_rng(3)
+    for mode, A in ((2, 5), (0, 4)):
+        for autoreset in (0, 1):
+            n, steps = 77, 9
+            kw = dict(n_envs=n, seed=8, autoreset=autoreset, goal_mode=0, max_episode_steps=4 if autoreset else 0)
+            e1, e2 = HostEnv(K, _config(mode, False, **kw), warps=2), HostEnv(K, _config(mode, False, **kw), warps=3)
+            for e in (e1, e2):
+                e.companion("reset"); e.goal[:] = 0; e.goal[6] = 1; e.goal[0] = 0.1; e.goal[4] = -0.05
+            acts = rng.uniform(-1, 1, (steps, n, A)).astype(np.float32)
+            obs_r, rew_r, done_r = e1.launch(acts, n_steps=steps, store=True)
+            for k in range(steps):
+                e2.launch(acts[k])
+                assert np.array_equal(e2.obs, obs_r[k]) and np.array_equal(e2.reward, rew_r[k]) and np.array_equal(e2.done, done_r[k]), (mode, k)
+            for name in ("state", "integ", "params", "ep_length", "ep_index"):
+                assert np.array_equal(getattr(e1, name), getattr(e2, name)), (mode, name)
