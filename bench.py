@@ -144,9 +144,9 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             # same workload as the CUDA arm (CoupledWrapper env.step under U(-1,1) actions with the trainer's reset
             # protocol and mode-0 goals); the envs are stepped one per host core instead of 2^21 per GPU
-            "config": {"workload": "CoupledWrapper env.step, U(-1,1) actions, trajgen mode-0 goals, reset on termination "
-                                   "(4000-step limit): the reference's CPU path (numpy RHS + scipy solve_ivp DOP853), "
-                                   "one env per host core, bounded sample",
+            "config": {"workload": "CoupledWrapper env.step, U(-1,1) actions, reset on termination: the reference's CPU "
+                                   "path (numpy RHS + scipy solve_ivp DOP853), one env per host core, bounded sample "
+                                   "(fixed goal: the trajectory generator's per-step goal update is not in the sample)",
                        "framework": "MONO", "actions": "random", "envs_per_gpu": args.envs_per_gpu},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
