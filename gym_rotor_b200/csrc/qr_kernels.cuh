@@ -139,7 +139,7 @@ __device__ __noinline__ void auto_reset_env(const StepArgs<T>* ap, int64_t e, ui
         T ts[12];
         uint32_t rnd[4];
         ph((uint32_t)gid, (uint32_t)(gid >> 32), episode, QR_DOMAIN_RESET + 5u, rnd);
-        traj_restart<T>(c.goal_mode, r, ts, r.goal, u01t<T>(rnd[0]), u01t<T>(rnd[1]), c.dt);
+        traj_restart<T, false>(c.goal_mode, r, ts, r.goal, u01t<T>(rnd[0]), u01t<T>(rnd[1]), c.dt);   // hover / circle / eight (see qr_traj.cuh)
 #pragma unroll
         for (int i = 0; i < 12; ++i) a.traj[i * a.n + e] = ts[i];
     } else {
@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(QR_BLOCK) k_goal_update(const StepArgs<T> a)
 #pragma unroll
     for (int i = 0; i < 12; ++i) { ts[i] = a.traj[i * N + e]; goal[i] = a.goal[i * N + e]; }
     ensure_so3<T>(R);   // get_desired -> state_decomposition
-    traj_desired<T>(traj_ref_mode(a.c.goal_mode), x, v, R, W, ts, goal, (T)0, (T)0, a.c.dt);
+    traj_desired<T>(traj_ref_mode<>(a.c.goal_mode), x, v, R, W, ts, goal, (T)0, (T)0, a.c.dt);
 #pragma unroll
     for (int i = 0; i < 12; ++i) { a.traj[i * N + e] = ts[i]; a.goal[i * N + e] = goal[i]; }
 }

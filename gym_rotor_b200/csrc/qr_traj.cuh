@@ -35,7 +35,10 @@ template <typename T> QR_DEV void traj_start(const T* x, const T* R_so3, T* ts)
 
 // One get_desired(state, mode) call.  R must already be ensure_SO3'd.  u_ttraj / u_w: uniforms for the hover's
 // t_traj ~ U(2,5) and w_b1d ~ U(-0.15 pi, 0.15 pi), only read when the trajectory starts.
-template <typename T>
+// ALL_MODES = false leaves out take-off / land / stay (modes 2-4): that instantiation is the one inlined into the step
+// kernel's auto reset, whose code -- and with it the register allocation of the whole persistent loop -- stays exactly
+// what was profiled (profiles/r01u_*); qr_create therefore refuses autoreset together with those three goal modes.
+template <typename T, bool ALL_MODES = true>
 QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* W, T* ts, T* goal, T u_ttraj, T u_w, T dt)
 {
     using N = num<T>;
@@ -67,16 +70,16 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
             ts[8] = (T)2 + ((T)5 - (T)2) * u_ttraj;
             ts[7] = (T)6.907755278982137 / ts[8];                       // -log(0.001) / t_traj
             ts[6] = (T)-0.15 * PI + ((T)0.15 * PI - ((T)-0.15 * PI)) * u_w;
-        } else if (mode == 2) {
+        } else if (ALL_MODES && mode == 2) {
             // takeoff(): set_desired_states_to_zero (fresh float64 arrays), horizontal position held; t_traj is a
             // float32 expression (python float - np.float32, NEP 50)
 #pragma unroll
             for (int i = 0; i < 3; ++i) { xd[i] = 0; vd[i] = 0; }
             xd[0] = x[0]; xd[1] = x[1];
             ts[8] = (T)__fdiv_rn(__fsub_rn(-0.5f, (float)x[2]), -0.05f);   // (takeoff_end_height - z) / takeoff_velocity
-        } else if (mode == 3) {
+        } else if (ALL_MODES && mode == 3) {
             ts[8] = (T)__fdiv_rn(__fsub_rn(-0.25f, (float)x[2]), 1.0f);    // (landing_motor_cutoff_height - z) / landing_velocity
-        } else if (mode == 4) {
+        } else if (ALL_MODES && mode == 4) {
             // stay(): nothing else
         } else if (mode == 5) {
             ts[8] = (T)0.7 / (T)0.4 + (T)2 * (T)2 * PI / (T)0.4;         // radius / v + num_circles * 2 pi / W
@@ -84,9 +87,9 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
             ts[8] = (T)3 * (T)9; ts[6] = (T)0.349066;                   // num_of_eights * T ; eight_w_b1d
         }
     }
-    if (mode != 4) ts[0] = ts[0] + dt;   // update_current_time() is called by every mode function except stay()
+    if (!ALL_MODES || mode != 4) ts[0] = ts[0] + dt;   // update_current_time() is called by every mode function except stay()
     const T t = ts[0];
-    if (mode == 2) {
+    if (ALL_MODES && mode == 2) {
         // x_init is the float32 state handed in at the start: "x_init[2] + v t" is float32 arithmetic and "t < t_traj"
         // a float32 comparison (the python floats are cast, NEP 50)
         if ((float)t < (float)ts[8]) {
@@ -98,7 +101,7 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
                 flags |= 2;   // mark_traj_end(True): manual mode from the next call on
             }
         }
-    } else if (mode == 3) {
+    } else if (ALL_MODES && mode == 3) {
         if ((float)t < (float)ts[8]) {
             xd[2] = (T)__fadd_rn((float)ts[4], (float)((T)1 * t));
         } else if (x[2] > (T)-0.25) {
@@ -106,7 +109,7 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
         } else {
             xd[2] = (T)-0.25; vd[2] = (T)1;
         }
-    } else if (mode == 4) {
+    } else if (ALL_MODES && mode == 4) {
         flags |= 2;   // mark_traj_end(True)
     } else if (mode == 1) {
         const T k = ts[7], w = ts[6], ek = exp_t<T>(-k * t);
@@ -183,13 +186,14 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
 
 // reference mode numbers for the goal_mode values of the C ABI:
 // QR_GOAL_TRAJ_HOVER/CIRCLE/EIGHT/TAKEOFF/LAND/STAY = 2/3/4/5/6/7 -> trajectory_generator modes 1/5/6/2/3/4
-QR_DEV int traj_ref_mode(int goal_mode)
+template <bool ALL_MODES = true> QR_DEV int traj_ref_mode(int goal_mode)
 {
+    if (!ALL_MODES) return goal_mode == 2 ? 1 : (goal_mode == 3 ? 5 : 6);
     return goal_mode == 2 ? 1 : (goal_mode == 3 ? 5 : (goal_mode == 4 ? 6 : (goal_mode == 5 ? 2 : (goal_mode == 6 ? 3 : 4))));
 }
 
 // trajectory start from the float32-cast state (main.py:226-228): mark_traj_start + the first get_desired
-template <typename T>
+template <typename T, bool ALL_MODES = true>
 QR_DEV void traj_restart(int goal_mode, const EnvRegs<T>& e, T* ts, T* goal, T u_ttraj, T u_w, T dt)
 {
     T x[3], v[3], R[9], W[3];
@@ -201,7 +205,7 @@ QR_DEV void traj_restart(int goal_mode, const EnvRegs<T>& e, T* ts, T* goal, T u
     ensure_so3<T>(R);
     traj_start<T>(x, R, ts);
     goal[6] = 1; goal[7] = 0; goal[8] = 0;
-    traj_desired<T>(traj_ref_mode(goal_mode), x, v, R, W, ts, goal, u_ttraj, u_w, dt);
+    traj_desired<T, ALL_MODES>(traj_ref_mode<ALL_MODES>(goal_mode), x, v, R, W, ts, goal, u_ttraj, u_w, dt);
 }
 
 }  // namespace qr

@@ -183,6 +183,8 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     if (c->integrator == QR_INT_EULER && c->mode != QR_MODE_QUAD)
         return fail(QR_ERR_INVALID, "qr_create: the Euler integrator exists only for the base Quad-v0 env (quad.py:252)");
     if (c->goal_mode < QR_GOAL_EXTERNAL || c->goal_mode > QR_GOAL_TRAJ_STAY) return fail(QR_ERR_INVALID, "qr_create: bad goal_mode");
+    if (c->autoreset && c->goal_mode >= QR_GOAL_TRAJ_TAKEOFF)
+        return fail(QR_ERR_INVALID, "qr_create: autoreset is not available with the take-off / land / stay goal modes (reset them with qr_reset + qr_init_goal)");
     if (c->goal_mode != QR_GOAL_EXTERNAL && c->mode == QR_MODE_QUAD)
         return fail(QR_ERR_INVALID, "qr_create: on-device goal generation needs a wrapper mode");
     int ndev = 0;

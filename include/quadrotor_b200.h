@@ -43,7 +43,8 @@ enum { QR_ACT_POLICY = 2 };
 enum { QR_INT_DOP853 = 0, QR_INT_EULER = 1 };                            /* quad.py:62 */
 enum { QR_ENV_TRAIN = 0, QR_ENV_EVAL = 1 };                              /* reset(env_type=...) quad.py:171 */
 /* set_goal_state | on-device trajectory_generator: mode 0 (idle, evaluated inside qr_step), 1 hover, 5 circle, 6 figure
- * eight, 2 take-off, 3 land, 4 stay (utils/trajectory_generator.py:113-173, 252-505) */
+ * eight, 2 take-off, 3 land, 4 stay (utils/trajectory_generator.py:113-173, 252-505).  The last three cannot be
+ * combined with autoreset (reset such envs with qr_reset + qr_init_goal). */
 enum { QR_GOAL_EXTERNAL = 0, QR_GOAL_TRAJ_MODE0 = 1, QR_GOAL_TRAJ_HOVER = 2, QR_GOAL_TRAJ_CIRCLE = 3, QR_GOAL_TRAJ_EIGHT = 4,
        QR_GOAL_TRAJ_TAKEOFF = 5, QR_GOAL_TRAJ_LAND = 6, QR_GOAL_TRAJ_STAY = 7 };
 /* per-env status bits (the reference raises / ignores sol.status instead: coupled:63-64) */
