@@ -58,6 +58,31 @@ def test_no_device_fails_loudly():
     assert rc != 0 and b"no CUDA device" in L.qr_last_error()
 
 
+def test_create_rejects_inconsistent_configs():
+    """Argument checks of qr_create come before the device is touched: they can be exercised anywhere."""
+    from gym_rotor_b200 import _native
+    L = _native.load()
+    h = ctypes.c_void_p()
+
+    def rc_for(mode=1, **kw):
+        c = _native.QrConfig()
+        L.qr_default_config(ctypes.byref(c), mode, 0)
+        c.n_envs = 64
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return L.qr_create(ctypes.byref(c), 0, ctypes.byref(h)), L.qr_last_error()
+    rc, msg = rc_for(n_envs=0)
+    assert rc == 1 and b"n_envs" in msg
+    rc, msg = rc_for(goal_mode=_native.GOAL_TRAJ_STAY + 1)
+    assert rc == 1 and b"goal_mode" in msg
+    rc, msg = rc_for(goal_mode=_native.GOAL_TRAJ_TAKEOFF, autoreset=1)       # modes 2-4 are not in the kernel's reset path
+    assert rc == 1 and b"autoreset" in msg
+    rc, msg = rc_for(mode=0, goal_mode=_native.GOAL_TRAJ_MODE0)              # on-device goals need a wrapper mode
+    assert rc == 1 and b"wrapper" in msg
+    rc, msg = rc_for(mode=1, integrator=_native.INT_EULER)                   # Euler exists for Quad-v0 only (quad.py:252)
+    assert rc == 1 and b"Euler" in msg
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under gym_rotor_b200/ may reference it."""
     pkg = os.path.join(ROOT, "gym_rotor_b200")
