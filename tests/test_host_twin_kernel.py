@@ -104,7 +104,7 @@ class HostEnv:
         assert self.K.tw_companion(C.byref(self.cfg), C.byref(b), {"reset": 0, "init_goal": 1, "goal_update": 2,
                                                                  "norm_error_state": 3}[which], mp, env_type) == 0
 
-    def launch(self, actions=None, n_steps=1, store=False):
+    def launch(self, actions=None, n_steps=1, store=False, lo=0, hi=None):
         b = self._arrays()
         keep = []
         policy = isinstance(actions, str) and actions == "policy"
@@ -118,7 +118,7 @@ class HostEnv:
             out = (np.zeros((n_steps, self.n, self.O), np.float32), np.zeros((n_steps, self.n, self.G), self.T),
                    np.zeros((n_steps, self.n, self.G), np.uint8))
             b.obs_roll, b.reward_roll, b.done_roll = (x.ctypes.data for x in out)
-        rc = self.K.tw_kstep(C.byref(self.cfg), C.byref(b), 0, self.n, int(n_steps), self.warps, int(policy))
+        rc = self.K.tw_kstep(C.byref(self.cfg), C.byref(b), int(lo), self.n if hi is None else int(hi), int(n_steps), self.warps, int(policy))
         assert rc == 0
         return out
 
@@ -442,3 +442,35 @@ def test_kernel_modul_quad_rollouts_and_external_goals(libs):
                 assert np.array_equal(e2.obs, obs_r[k]) and np.array_equal(e2.reward, rew_r[k]) and np.array_equal(e2.done, done_r[k]), (mode, k)
             for name in ("state", "integ", "params", "ep_length", "ep_index"):
                 assert np.array_equal(getattr(e1, name), getattr(e2, name)), (mode, name)
+
+
+def test_kernel_edge_cases(libs):
+    """Non-finite state flagged (scipy would raise), tiny handles, and launches over sub-ranges of the envs (what
+    qr_step_host's chunked pipeline issues) == one launch over all of them."""
+    import quad_oracle as qo
+    K, _ = libs
+    rng = np.random.default_rng(0)
+    n = 64
+    st, ig, par = qo.COracle("MONO").reset_from_uniforms(rng.random((n, 20)))
+    goal = np.zeros((n, 12)); goal[:, 6] = 1.0
+    act = rng.uniform(-1, 1, (n, 4))
+    bad = st.copy(); bad[5, 2] = np.nan
+    env = HostEnv(K, _config(1, n_envs=n))
+    env.set_state(bad, ig, par, goal)
+    env.launch(act)
+    assert env.status[5] & 1 and (np.delete(env.status, 5) == 0).all()
+    assert np.isfinite(np.delete(env.state.T, 5, axis=0)).all() and env.stats[8] == 1
+    # the other envs are what a clean launch gives
+    ref = HostEnv(K, _config(1, n_envs=n)); ref.set_state(st, ig, par, goal); ref.launch(act)
+    keep = np.arange(n) != 5
+    assert np.array_equal(env.state[:, keep], ref.state[:, keep]) and np.array_equal(env.obs[keep], ref.obs[keep])
+    # sub-range launches (ragged boundaries, not multiples of 32)
+    parts = HostEnv(K, _config(1, n_envs=n)); parts.set_state(st, ig, par, goal)
+    for lo, hi in ((0, 19), (19, 50), (50, 64)):
+        parts.launch(act, lo=lo, hi=hi)
+    for name in ("state", "integ", "obs", "reward", "done", "nfev"):
+        assert np.array_equal(getattr(parts, name), getattr(ref, name)), name
+    # tiny handles
+    for m in (1, 5):
+        tiny = HostEnv(K, _config(1, n_envs=m), warps=1); tiny.set_state(st[:m], ig[:m], par[:m], goal[:m]); tiny.launch(act[:m])
+        assert np.array_equal(tiny.state, ref.state[:, :m]) and np.array_equal(tiny.obs, ref.obs[:m])
