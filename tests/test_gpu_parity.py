@@ -318,58 +318,6 @@ def test_step_host_equals_device_step():
     e1.close(); e2.close()
 
 
-def test_stepping_is_sharding_independent():
-    """rank g owns a block of global env ids and every random draw (resets, in-kernel actions) is keyed by
-    (seed, global env id, episode), so the envs must not care how they are split over handles / GPUs -- nor which
-    lane, tile or reset batch they land in.  One handle of 2^16 envs against four shards with env_id_offset, through
-    multi-step launches (reset inside the kernel) and single-step launches (queued resets), float32."""
-    n, K = 1 << 16, 40
-    kw = dict(seed=21, autoreset=True, goal_mode="traj0", max_episode_steps=25)
-    whole = _env(n, "MONO", torch.float32, **kw)
-    parts = [_env(n // 4, "MONO", torch.float32, env_id_offset=i * (n // 4), **kw) for i in range(4)]
-    for e in [whole] + parts:
-        e.reset(); e.init_goal(); e.get_norm_error_state()
-        e.rollout(K)                 # Philox actions drawn in the kernel
-        for _ in range(6):
-            e.rollout(1)
-    for name in ("state_soa", "integ_soa", "params_soa", "goal_soa"):
-        assert torch.equal(torch.cat([getattr(p, name) for p in parts], dim=1), getattr(whole, name)), name
-    for name in ("obs", "reward", "done", "ep_length"):
-        assert torch.equal(torch.cat([getattr(p, name) for p in parts], dim=0), getattr(whole, name)), name
-    sw = whole.stats(); sp = sum(p.stats() for p in parts)
-    assert sw[0] == sp[0] and sw[7] == sp[7] == (K + 6) * n and sw[0] > n     # episodes ended, env-steps
-    for e in [whole] + parts:
-        e.close()
-
-
-def test_full_size_invariants():
-    """BASELINE config size (2^21 envs on one GPU, float32, random actions, auto reset): properties that hold for any
-    number of envs -- step accounting, finite bounded observations, reward range, done => reward -1, R on SO(3)."""
-    n, steps = 1 << 21, 12
-    env = _env(n, "MONO", torch.float32, seed=3, autoreset=True, goal_mode="traj0", max_episode_steps=4000, diagnostics=False)
-    env.reset(); env.init_goal(); env.get_norm_error_state()
-    env.stats()
-    gen = torch.Generator(device="cuda:0"); gen.manual_seed(5)
-    ended = 0
-    for t in range(steps):
-        act = torch.rand((n, 4), device="cuda:0", generator=gen) * 2 - 1
-        obs, rew, done, _, _ = env.step(act)
-        o = obs[0]
-        assert bool(torch.isfinite(o).all()) and bool(torch.isfinite(rew).all())
-        # not done: inside the limits by the definition of done; done: replaced by the first observation of the new episode
-        assert bool((o[:, 0:3].abs() < 1).all()) and bool((o[:, 6:9].abs() < 1).all()) and bool((o[:, 20:23].abs() < 1).all())
-        d = done[:, 0]
-        assert bool((rew[d, 0] == -1).all()) and bool(((rew[~d, 0] >= 0) & (rew[~d, 0] <= 1)).all())
-        ended += int(d.sum())
-    s = env.stats()
-    assert s[7] == steps * n and s[0] == ended and ended > 0
-    assert int(env.status.max()) == 0
-    R = env.state_soa[6:15].t().reshape(n, 3, 3)          # rows of the column-major storage: R^T; orthogonality is symmetric
-    err = (R @ R.transpose(1, 2) - torch.eye(3, device="cuda:0")).abs().max()
-    assert float(err) < 1e-3
-    env.close()
-
-
 def test_random_action_rollout_statistics():
     """In-kernel Philox actions + auto reset: the DOP853 attempt histogram and episode length look like the
     reference's under random actions (~94 % single attempt, mean episode ~110 steps)."""
@@ -468,8 +416,10 @@ def test_status_flags_nonfinite_state():
     env.close()
 
 
-@pytest.mark.parametrize("name,gm", [("hover", "hover"), ("circle", "circle"), ("eight", "eight"), ("circle_manual", "circle"),
-                                     ("takeoff", "takeoff"), ("land", "land"), ("land_low", "land"), ("stay", "stay")])
+TRAJ_CASES = [("hover", "hover"), ("circle", "circle"), ("eight", "eight"), ("circle_manual", "circle")]
+
+
+@pytest.mark.parametrize("name,gm", TRAJ_CASES)
 def test_trajectory_modes_match_reference(name, gm):
     """qr_init_goal + qr_goal_update (modes 1 - 6 and the manual fallback) call by call against the reference's
     TrajectoryGenerator driven along a real flight (tests/golden/traj_modes.npz)."""

@@ -99,54 +99,6 @@ def test_compiled_actor_in_the_loop_flies_the_reference_episode():
     env.close()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("fw,tag", [("MONO", "mono"), ("MODUL", "modul")])
-def test_fused_policy_rollout_flies_the_reference_episode(fw, tag):
-    """qr_rollout(act_dtype = QR_ACT_POLICY): the evaluation loop obs -> shipped actor -> env.step of main.py:304-365
-    in ONE launch, 1000 steps, against the episode the reference flew (KAT-2); bit-identical to the two-kernel loop
-    (qr_policy_td3 + qr_step).  The same test runs on the CPU emulator in tests/test_host_twin_kernel.py."""
-    from gym_rotor_b200 import vec_env
-    ep = np.load(os.path.join(G, "eval_%s.npz" % tag))
-    H, n = len(ep["reward"]), 64
-
-    def fresh():
-        env = vec_env.BatchedQuadEnv(n, framework=fw, dtype=torch.float64, goal_mode="traj0")
-        env.set_state(np.tile(ep["state0"], (n, 1)), np.tile(ep["integ0"], (n, 1)), np.tile(ep["params"], (n, 1)),
-                      np.tile(ep["goal0"], (n, 1)))
-        env.obs.copy_(torch.as_tensor(np.tile(ep["obs0"], (n, 1)), device="cuda:0"))
-        return env
-    fused = fresh()
-    obs_r, rew_r, done_r = fused.rollout(H, actions="policy", store=True)
-    assert not bool(done_r.any())
-    st = fused.get_state()[0]
-    assert np.abs(st[0] - ep["state"][-1]).max() < 1e-3 and np.abs(st - st[0]).max() == 0.0
-    ret = rew_r[:, 0, :].sum(dim=0).cpu().numpy()
-    assert np.abs(ret - ep["reward"].sum(axis=0)).max() < 0.05 and ret[0] > 985
-    loop = fresh()
-    for t in range(50):
-        o_n, rew, done, _, _ = loop.step(loop.policy_td3())
-        assert torch.equal(torch.cat(o_n, dim=1), obs_r[t]) and torch.equal(rew, rew_r[t]), t
-    fused.close(); loop.close()
-
-
-@pytest.mark.gpu
-def test_reference_attribute_surface_on_device():
-    """What the reference's callers read off the env object: spaces, limits, force constants, matrices."""
-    from gym_rotor_b200 import vec_env
-    env = vec_env.BatchedQuadEnv(8, framework="MODUL", dtype=torch.float32)
-    env.reset()
-    assert env.action_space.shape == (5,) and env.observation_space.shape == (18,)
-    env.action_space.seed(1); env.observation_space.seed(1)          # utils/utils.py:17-18
-    assert (env.x_lim, env.v_lim, env.eIx_lim, env.eIb1_lim, env.dt) == (1.0, 4.0, 3.0, 3.0, 1.0 / 200)
-    m, c_tw = env.params_soa[0], env.params_soa[5]
-    assert torch.allclose(env.hover_force, m * 9.81 / 4) and torch.allclose(env.max_force, c_tw * env.hover_force)
-    assert torch.allclose(env.scale_act + env.avrg_act, env.max_force)
-    A, Ainv = env.forces_to_fM, env.fM_to_forces
-    assert A.shape == (8, 4, 4) and float((A @ Ainv - torch.eye(4, dtype=torch.float64, device=A.device)).abs().max()) < 1e-12
-    assert env.J_nominal.shape == (3, 3)
-    env.close()
-
-
 def test_reference_attribute_surface_without_gymnasium():
     """Box stand-in (set_seed seeds both spaces, utils/utils.py:17-18) and forces_to_fM / fM_to_forces (quad.py:396-402)."""
     from gym_rotor_b200.vec_env import Box, forces_to_fM_matrices
