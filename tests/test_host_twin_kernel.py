@@ -474,3 +474,22 @@ def test_kernel_edge_cases(libs):
     for m in (1, 5):
         tiny = HostEnv(K, _config(1, n_envs=m), warps=1); tiny.set_state(st[:m], ig[:m], par[:m], goal[:m]); tiny.launch(act[:m])
         assert np.array_equal(tiny.state, ref.state[:, :m]) and np.array_equal(tiny.obs, ref.obs[:m])
+
+
+def test_kernel_experimental_e3_from_b_keeps_parity(libs, tmp_path):
+    """QR_E3_FROM_B (compile-time experiment, off in the product build): forming the third-order error sums from the
+    B-weighted sums plus three correction terms changes rounding only -- the golden parity bars still hold."""
+    K = _build("twin_kernel.cpp", str(tmp_path), "libtwink_e3.so", defines=("QR_E3_FROM_B=1",))
+    K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
+    for fw, tag, mode in (("MONO", "mono", 1), ("MODUL", "modul", 2)):
+        g = np.load(os.path.join(G, "step_%s_a64.npz" % tag))
+        n = g["action"].shape[0]
+        env = HostEnv(K, _config(mode, n_envs=n))
+        env.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
+        env.launch(np.ascontiguousarray(g["action"], np.float64))
+        assert _relerr(env.state.T, g["state_out"]) <= 1e-12 and (env.nfev == g["nfev"]).all()
+        assert int((env.obs.view(np.uint32) != g["obs"].view(np.uint32)).sum()) <= 3
+        e32 = HostEnv(K, _config(mode, dtype64=False, n_envs=n), warps=12)
+        e32.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
+        e32.launch(g["action"].astype(np.float32))
+        assert np.abs(e32.state.T - g["state_out"]).max() <= 1e-5 and ((e32.nfev - 2) // 12 != (g["nfev"] - 2) // 12).mean() <= 0.03
