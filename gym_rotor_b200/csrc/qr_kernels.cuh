@@ -19,6 +19,11 @@
 #ifndef QR_TILE_PREFETCH
 #define QR_TILE_PREFETCH 0
 #endif
+// experimental (off: not measured yet): write the per-lane observation rows and the released state with streaming
+// stores (st.global.cs): the data is not read again by this launch
+#ifndef QR_STREAM_STORES
+#define QR_STREAM_STORES 0
+#endif
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
@@ -415,8 +420,13 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < O; ++i) tile[lane * O + i] = o[i];
                 } else {
                     if (obs1) {
+#if QR_STREAM_STORES
+#pragma unroll
+                        for (int i = 0; i < O; ++i) { if (!POLICY) __stcs(obs1 + i, o[i]); else obs1[i] = o[i]; }
+#else
 #pragma unroll
                         for (int i = 0; i < O; ++i) obs1[i] = o[i];
+#endif
                     }
                     if (obs2) {
 #pragma unroll
@@ -523,12 +533,21 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     // release the env: state back to HBM (not the terminal state of an env whose reset is queued)
                     if (!deferred) {
 #pragma unroll
+#if QR_STREAM_STORES
+                        for (int i = 0; i < 3; ++i) __stcs(a.state + i * N + e, x[i]);
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) __stcs(a.state + (3 + i) * N + e, y[i]);
+                        __stcs(a.state + 15 * N + e, y[12]); __stcs(a.state + 16 * N + e, y[13]); __stcs(a.state + 17 * N + e, W3);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) __stcs(a.integ + i * N + e, In[i]);
+#else
                         for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
 #pragma unroll
                         for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
                         a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) a.integ[i * N + e] = In[i];
+#endif
                     }
                     a.ep_return[e] = ep_ret0;
                     if (G == 2) a.ep_return[N + e] = ep_ret1;
