@@ -24,6 +24,10 @@
 #ifndef QR_STREAM_STORES
 #define QR_STREAM_STORES 0
 #endif
+// experimental (off: not measured yet): fetch the next env's state with streaming loads (ld.global.cs)
+#ifndef QR_STREAM_LOADS
+#define QR_STREAM_LOADS 0
+#endif
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
@@ -323,10 +327,17 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (ee < a.env_hi) {
                     has_next = true; e_next = ee;
                     // K0 and d are dead for a lane that is idle or has finished its step (A1 only reads ode's counters)
+#if QR_STREAM_LOADS
+                    d.fm = __ldcs(a.state + 0 * N + ee); d.g = __ldcs(a.state + 1 * N + ee); d.Mi0 = __ldcs(a.state + 2 * N + ee);
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) K0[i] = __ldcs(a.state + (3 + i) * N + ee);
+                    d.Mi1 = __ldcs(a.state + 17 * N + ee);
+#else
                     d.fm = a.state[0 * N + ee]; d.g = a.state[1 * N + ee]; d.Mi0 = a.state[2 * N + ee];
 #pragma unroll
                     for (int i = 0; i < 14; ++i) K0[i] = a.state[(3 + i) * N + ee];
                     d.Mi1 = a.state[17 * N + ee];
+#endif
                     if (a.actions) {
                         if (a.act_f32) {
                             const float* p = (const float*)a.actions + ee * A;

@@ -166,6 +166,7 @@ static inline int __ffs(int v) { return __builtin_ffs(v); }
 template <typename T> static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
+template <typename T> static inline T __ldcs(const T* p) { return *p; }
 static inline void __threadfence() {}
 static inline void __syncthreads() { fprintf(stderr, "simt: __syncthreads is not emulated (one warp at a time)\n"); abort(); }
 using std::min;
