@@ -44,7 +44,9 @@ def _build(src, tmp, name, opt="-O1", defines=()):
 @pytest.fixture(scope="module")
 def libs(tmp_path_factory):
     tmp = str(tmp_path_factory.mktemp("twink"))
-    K = _build("twin_kernel.cpp", tmp, "libtwink.so")
+    # QR_TWIN_DEFINES="QR_E3_FROM_B=1,QR_TILE_PREFETCH=1": run the whole file against an experimental kernel variant
+    extra = tuple(d for d in os.environ.get("QR_TWIN_DEFINES", "").split(",") if d)
+    K = _build("twin_kernel.cpp", tmp, "libtwink.so", defines=extra)
     K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
     K.tw_actor.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     K.tw_companion.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int, C.c_void_p, C.c_int]
