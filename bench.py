@@ -174,7 +174,7 @@ def run_ours(args):
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     n = args.envs_per_gpu
     env = vec_env.BatchedQuadEnv(n, framework=fw, dtype=dtype, device=dev, seed=args.seed, autoreset=True,
-                                 goal_mode="traj0" if fw != "QUAD" else "external",
+                                 goal_mode=(args.goal if fw != "QUAD" else "external"),
                                  env_type="eval" if args.policy else "train", max_episode_steps=1000 if args.policy else 4000,
                                  env_id_offset=rank * n, diagnostics=False)
     env.reset(env_type="eval" if args.policy else "train")
@@ -277,9 +277,10 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "%s env.step, %d envs/GPU (2^24 over 8 GPUs), U(-1,1) actions resident in HBM, "
-                                   "on-device trajgen mode-0 goals, in-kernel auto reset (4000-step limit), "
+                                   "on-device trajgen %s goals, in-kernel auto reset (4000-step limit), "
                                    "stats all-reduce every %d steps" % (
-                                       {"MONO": "CoupledWrapper", "MODUL": "DecoupledWrapper", "QUAD": "Quad-v0"}[fw], n, STATS_EVERY),
+                                       {"MONO": "CoupledWrapper", "MODUL": "DecoupledWrapper", "QUAD": "Quad-v0"}[fw], n,
+                                       {"traj0": "mode-0"}.get(args.goal, args.goal), STATS_EVERY),
                        "envs_per_gpu": n, "framework": fw, "actions": ("shipped TD3 actor in the loop (qr_policy_td3, compiled effective weights)" if args.policy else args.actions),
                        "fused_steps_per_launch": fused,
                        "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2)" % (bytes_per * n / 1e6),
@@ -325,6 +326,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--actions", default="random", choices=["random", "zero"])
     ap.add_argument("--policy", action="store_true", help="config 5: the shipped TD3 actor in the loop")
+    ap.add_argument("--goal", default="traj0", choices=["traj0", "hover", "circle", "eight"],
+                    help="on-device trajectory generator mode (config 4: traj0; 'eight' etc. = trajectory tracking, one extra "
+                         "goal-update kernel per step)")
     ap.add_argument("--fused", type=int, default=1, help="env.step() calls fused per launch (qr_rollout, in-kernel actions)")
     args = ap.parse_args()
     if args.warmup < 3:
