@@ -34,7 +34,6 @@
 namespace qr {
 
 constexpr int QR_BLOCK = 128;        // companion kernels (reset, goal init, observation)
-constexpr int QR_MAX_THREADS = 384;  // step kernel: up to 12 persistent warps per SM (float32; 6 warps in float64)
 #ifndef QR_STEP_THREADS_F32
 #define QR_STEP_THREADS_F32 384
 #endif
@@ -119,13 +118,6 @@ QR_DEV void cp_async_commit() {}
 template <int N> QR_DEV void cp_async_wait_group() {}
 #endif
 template <typename T> QR_DEV int32_t& stash_i32(T* sh, int slot) { return *reinterpret_cast<int32_t*>(sh + slot * 32); }
-
-QR_DEV double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // ---- auto reset, out of line (rare: once per episode) ---------------------------------------------------------
 // env.reset -> trajectory_generator.mark_traj_start/get_desired -> set_goal_state -> get_norm_error_state
@@ -236,7 +228,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     constexpr int A = (MODE == 2) ? 5 : 4;
     constexpr int G = (MODE == 2) ? 2 : 1;
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const EnvConst<T>& c = a.c;
     const int64_t N = a.n;
     unsigned char* wbase = smem_raw + warp * warp_smem<T>::bytes;
@@ -251,7 +243,6 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 
     // 32-env tiles are handed out dynamically (one atomic per tile on a per-launch counter): warps that drew
     // cheap envs simply take more tiles, so the persistent grid drains evenly
-    (void)wpb;
     const int64_t n_range = a.env_hi - a.env_lo;
     const int64_t ntiles = (n_range + 31) >> 5;
     int64_t tile_base = 0;    // warp-uniform: first env of the tile currently being handed out
