@@ -495,3 +495,29 @@ def test_kernel_experimental_e3_from_b_keeps_parity(libs, tmp_path):
         e32.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
         e32.launch(g["action"].astype(np.float32))
         assert np.abs(e32.state.T - g["state_out"]).max() <= 1e-5 and ((e32.nfev - 2) // 12 != (g["nfev"] - 2) // 12).mean() <= 0.03
+
+
+def test_kernel_fp64_free_running_vs_c_oracle(libs):
+    """State fed back for 300 steps without re-synchronisation (the north-star bar: <= 1e-9 after the horizon on envs
+    still alive), attempt counts and done flags identical step by step."""
+    import quad_oracle as qo
+    K, _ = libs
+    n = 48
+    rng = np.random.default_rng(4)
+    orc = qo.COracle("MONO")
+    st_o, ig_o, par = orc.reset_from_uniforms(rng.random((n, 20)))
+    goal = np.zeros((n, 12)); goal[:, 6] = 1.0
+    env = HostEnv(K, _config(1, n_envs=n), warps=2)
+    env.set_state(st_o, ig_o, par, goal)
+    alive = np.ones(n, bool)
+    for t in range(300):
+        act = rng.uniform(-1, 1, (n, 4)) * 0.3
+        obs_o, rew_o, done_o, nfev_o, _ = orc.step(st_o, ig_o, par, goal, act)
+        env.launch(act)
+        d = np.asarray(done_o).reshape(n, -1)[:, 0].astype(bool)
+        assert (env.nfev[alive] == nfev_o[alive]).all() and (env.done[alive, 0].astype(bool) == d[alive]).all(), t
+        alive &= ~d
+        if not alive.any():
+            break
+        assert _relerr(env.state.T[alive], st_o[alive]) <= 1e-9, t
+    assert t > 50
