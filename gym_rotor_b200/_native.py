@@ -26,7 +26,7 @@ STAT_NAMES = ["episodes", "return0", "return1", "length", "crashed", "truncated"
 # every symbol include/quadrotor_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = ["qr_default_config", "qr_create", "qr_destroy", "qr_get_config", "qr_get_buffers", "qr_reset",
            "qr_init_goal", "qr_goal_update", "qr_norm_error_state", "qr_policy_td3", "qr_step", "qr_rollout", "qr_step_host", "qr_set_state_host",
-           "qr_get_state_host", "qr_stats", "qr_launch_count", "qr_last_error", "qr_abi_version"]
+           "qr_get_state_host", "qr_stats", "qr_launch_count", "qr_last_error", "qr_abi_version", "qr_obs_stride"]
 
 
 class QrConfig(C.Structure):
@@ -85,6 +85,8 @@ def load():
     L.qr_launch_count.restype = C.c_int64
     L.qr_last_error.restype = C.c_char_p
     L.qr_abi_version.restype = C.c_int
+    L.qr_obs_stride.argtypes = [vp]
+    L.qr_obs_stride.restype = C.c_int
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

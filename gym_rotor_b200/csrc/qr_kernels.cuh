@@ -28,6 +28,13 @@
 #ifndef QR_STREAM_LOADS
 #define QR_STREAM_LOADS 0
 #endif
+// experimental (off: not measured yet): rows of the obs / final_obs buffers padded to a multiple of 4 floats (23 -> 24,
+// 18 -> 20), so that a lane writes its row as 16-byte vectors instead of 23 scattered 4-byte stores.  qr_obs_stride()
+// reports the row stride to the host side; rollout storage handed in by the caller stays dense.
+#ifndef QR_OBS_PAD
+#define QR_OBS_PAD 0
+#endif
+__host__ __device__ constexpr int obs_stride_of(int O) { return QR_OBS_PAD ? ((O + 3) & ~3) : O; }
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
@@ -225,6 +232,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int O = (MODE == 1) ? 23 : 18;
+    constexpr int OS = obs_stride_of(O);   // row stride of a.obs / a.final_obs
     constexpr int A = (MODE == 2) ? 5 : 4;
     constexpr int G = (MODE == 2) ? 2 : 1;
     constexpr unsigned FULL = 0xffffffffu;
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const int64_t e_first = __shfl_sync(FULL, e, 0);
             const int k_first = __shfl_sync(FULL, k, 0);
             const bool same = __all_sync(FULL, e - lane == e_first && k == k_first);   // (no warp primitive behind a short-circuit)
-            const bool coop = finmask == FULL && same && (e_first & 3) == 0 &&
+            const bool coop = !QR_OBS_PAD && finmask == FULL && same && (e_first & 3) == 0 &&
                               (!a.obs_roll || ((reinterpret_cast<uintptr_t>(a.obs_roll) + (size_t)(((int64_t)k * N + e_first) * O) * 4) & 15) == 0);
             if (fin) {
                 float o[23];
@@ -414,13 +422,34 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 // full sectors; measured 5 % faster than a general coalescing copy through shared memory).  When the
                 // whole warp finishes 32 consecutive envs together (`coop`: the lock-step regime of a trained
                 // policy), the rows go through a shared tile and leave as 16-byte stores of one contiguous block.
-                obs1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : ((last || POLICY) ? a.obs + e * O : nullptr);
-                obs2 = (a.obs_roll && (last || POLICY)) ? a.obs + e * O : nullptr;   // POLICY: the actor reads a.obs at the next sub-step
+                obs1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : ((last || POLICY) ? a.obs + e * OS : nullptr);
+                obs2 = (a.obs_roll && (last || POLICY)) ? a.obs + e * OS : nullptr;   // POLICY: the actor reads a.obs at the next sub-step
                 if (coop) {
                     float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
 #pragma unroll
                     for (int i = 0; i < O; ++i) tile[lane * O + i] = o[i];
                 } else {
+#if QR_OBS_PAD
+                    {   // rows inside a.obs are 16-byte aligned and padded: vector stores; caller's rollout storage: scalar
+                        float op[OS];
+#pragma unroll
+                        for (int i = 0; i < OS; ++i) op[i] = (i < O) ? o[i] : 0.f;
+                        float* rows[2] = {obs1, obs2};
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+                            float* row = rows[w];
+                            if (!row) continue;
+                            if (a.obs_roll && w == 0) {
+#pragma unroll
+                                for (int i = 0; i < O; ++i) row[i] = o[i];
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < OS / 4; ++i)
+                                    reinterpret_cast<float4*>(row)[i] = make_float4(op[4 * i], op[4 * i + 1], op[4 * i + 2], op[4 * i + 3]);
+                            }
+                        }
+                    }
+#else
                     if (obs1) {
 #if QR_STREAM_STORES
 #pragma unroll
@@ -434,6 +463,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 #pragma unroll
                         for (int i = 0; i < O; ++i) obs2[i] = o[i];
                     }
+#endif
                 }
                 rew0f = (float)rew[0];
                 ep_ret0 += (T)rew[0];
@@ -455,7 +485,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     ep_len_done = ep_len; ret_done0 = ep_ret0; ret_done1 = ep_ret1;
                     if (last) {
 #pragma unroll
-                        for (int i = 0; i < O; ++i) a.final_obs[e * O + i] = o[i];
+                        for (int i = 0; i < O; ++i) a.final_obs[e * OS + i] = o[i];
                     }
                     ep_idx += 1;
                     ep_ret0 = 0; ep_ret1 = 0; ep_len = 0;
@@ -593,8 +623,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (lane < n_now) {
                     do_reset = true; r_e = (int64_t)rq[rq_n - n_now + lane];
                     r_ep = __ldcg(a.ep_index + r_e);   // written when the env was released (already incremented)
-                    r_o1 = a.obs_roll ? a.obs_roll + r_e * O : a.obs + r_e * O;
-                    r_o2 = a.obs_roll ? a.obs + r_e * O : nullptr;
+                    r_o1 = a.obs_roll ? a.obs_roll + r_e * O : a.obs + r_e * OS;
+                    r_o2 = a.obs_roll ? a.obs + r_e * OS : nullptr;
                 }
                 rq_n -= n_now;
             }
@@ -725,7 +755,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 // thread, or by its warp through the shared tile / by an earlier launch)
                 float xo[23], af[5];
 #pragma unroll
-                for (int i = 0; i < O; ++i) xo[i] = a.obs[e * O + i];
+                for (int i = 0; i < O; ++i) xo[i] = a.obs[e * OS + i];
                 if (MODE == 1) actor_td3_mono(xo, af);
                 else { actor_td3_modul1(xo, af); actor_td3_modul2(xo + 15, af + 4); }
 #pragma unroll
@@ -903,7 +933,8 @@ __global__ void __launch_bounds__(QR_BLOCK) k_norm_error_state(const StepArgs<T>
 #pragma unroll
         for (int i = 0; i < 8; ++i) a.integ[i * a.n + e] = r.I[i];
     }
-    for (int i = 0; i < O; ++i) a.obs[e * O + i] = o[i];
+    const int OS = obs_stride_of(O);
+    for (int i = 0; i < O; ++i) a.obs[e * OS + i] = o[i];
 }
 
 // ---- the reference's shipped TD3 actors, obs -> action on device (agent.choose_action(obs, explor_noise_std=0),
@@ -915,17 +946,18 @@ __global__ void __launch_bounds__(QR_BLOCK) k_actor_td3(const float* __restrict_
 {
     constexpr int O = (MODE == 1) ? 23 : 18;
     constexpr int A = (MODE == 2) ? 5 : 4;
-    __shared__ float tile[QR_BLOCK * O];
+    constexpr int OS = obs_stride_of(O);
+    __shared__ float tile[QR_BLOCK * OS];
     const int tid = threadIdx.x;
     const int64_t e0 = (int64_t)blockIdx.x * QR_BLOCK;
     const int64_t rem = n - e0;
     const int nvalid = (int)(rem < QR_BLOCK ? rem : QR_BLOCK);
-    for (int i = tid; i < nvalid * O; i += QR_BLOCK) tile[i] = obs[e0 * O + i];
+    for (int i = tid; i < nvalid * OS; i += QR_BLOCK) tile[i] = obs[e0 * OS + i];
     __syncthreads();
     if (tid >= nvalid) return;
     float x[O], a[A];
 #pragma unroll
-    for (int i = 0; i < O; ++i) x[i] = tile[tid * O + i];
+    for (int i = 0; i < O; ++i) x[i] = tile[tid * OS + i];
     if (MODE == 1) {
         actor_td3_mono(x, a);
         *reinterpret_cast<float4*>(act + (e0 + tid) * 4) = make_float4(a[0], a[1], a[2], a[3]);

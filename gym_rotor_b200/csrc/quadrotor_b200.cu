@@ -150,6 +150,7 @@ int check(const qr_handle* h)
 extern "C" {
 
 int qr_abi_version(void) { return QR_ABI_VERSION; }
+int qr_obs_stride(const qr_handle* h) { return h ? obs_stride_of(h->O) : 0; }
 const char* qr_last_error(void) { return g_err.c_str(); }
 int64_t qr_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -204,8 +205,8 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     const size_t n = (size_t)c->n_envs, E = (size_t)h->elem;
     struct { void** p; size_t bytes; } allocs[] = {
         {&h->state, 18 * n * E}, {&h->integ, 8 * n * E}, {&h->params, 6 * n * E}, {&h->goal, 12 * n * E}, {&h->traj, 12 * n * E},
-        {(void**)&h->obs, n * h->O * 4}, {&h->reward, n * h->G * E}, {(void**)&h->done, n * h->G},
-        {(void**)&h->terminated, n}, {(void**)&h->truncated, n}, {(void**)&h->final_obs, n * h->O * 4},
+        {(void**)&h->obs, n * obs_stride_of(h->O) * 4}, {&h->reward, n * h->G * E}, {(void**)&h->done, n * h->G},
+        {(void**)&h->terminated, n}, {(void**)&h->truncated, n}, {(void**)&h->final_obs, n * obs_stride_of(h->O) * 4},
         {(void**)&h->nfev, n * 4}, {(void**)&h->status, n}, {&h->ep_return, 2 * n * E}, {(void**)&h->ep_length, n * 4},
         {(void**)&h->ep_index, n * 4}, {(void**)&h->stats, QR_NUM_STATS * sizeof(double)},
         {(void**)&h->tile_counter, 2 * sizeof(unsigned long long)}};
@@ -423,7 +424,12 @@ int qr_step_host(qr_handle* h, const void* actions_host, int act_dtype, float* o
         if (h->cfg.dtype == QR_F64) rc = launch_step<double>(h, lo, hi, h->d_actions, act_dtype, 1, nullptr, nullptr, nullptr, cs);
         else rc = launch_step<float>(h, lo, hi, h->d_actions, act_dtype, 1, nullptr, nullptr, nullptr, cs);
         if (rc) return rc;
-        if (obs_host) QR_CUDA(cudaMemcpyAsync(obs_host + (size_t)lo * h->O, h->obs + (size_t)lo * h->O, (size_t)(hi - lo) * h->O * 4, cudaMemcpyDeviceToHost, cs));
+        if (obs_host) {
+            const int OS = obs_stride_of(h->O);
+            if (OS == h->O) QR_CUDA(cudaMemcpyAsync(obs_host + (size_t)lo * h->O, h->obs + (size_t)lo * h->O, (size_t)(hi - lo) * h->O * 4, cudaMemcpyDeviceToHost, cs));
+            else QR_CUDA(cudaMemcpy2DAsync(obs_host + (size_t)lo * h->O, (size_t)h->O * 4, h->obs + (size_t)lo * OS, (size_t)OS * 4,
+                                           (size_t)h->O * 4, (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs));   // padded rows (QR_OBS_PAD)
+        }
         if (reward_host) QR_CUDA(cudaMemcpyAsync((char*)reward_host + (size_t)lo * h->G * h->elem, (char*)h->reward + (size_t)lo * h->G * h->elem,
                                                  (size_t)(hi - lo) * h->G * h->elem, cudaMemcpyDeviceToHost, cs));
         if (done_host) QR_CUDA(cudaMemcpyAsync(done_host + (size_t)lo * h->G, h->done + (size_t)lo * h->G, (size_t)(hi - lo) * h->G, cudaMemcpyDeviceToHost, cs));

@@ -110,12 +110,13 @@ class BatchedQuadEnv:
         self.params_soa = _view(b.params, (6, N), ts, d)
         self.goal_soa = _view(b.goal, (12, N), ts, d)
         self.traj_soa = _view(b.traj, (12, N), ts, d)
-        self.obs = _view(b.obs, (N, O), "<f4", d)
+        S = int(self._L.qr_obs_stride(self._h))   # row stride of the observation buffers (O unless built with padded rows)
+        self.obs = _view(b.obs, (N, S), "<f4", d)[:, :O]
         self.reward = _view(b.reward, (N, G), ts, d)
         self.done = _view(b.done, (N, G), "|u1", d)
         self.terminated = _view(b.terminated, (N,), "|u1", d)
         self.truncated = _view(b.truncated, (N,), "|u1", d)
-        self.final_obs = _view(b.final_obs, (N, O), "<f4", d)
+        self.final_obs = _view(b.final_obs, (N, S), "<f4", d)[:, :O]
         self.nfev = _view(b.nfev, (N,), "<i4", d)
         self.status = _view(b.status, (N,), "|u1", d)
         self.ep_return = _view(b.ep_return, (2, N), ts, d)

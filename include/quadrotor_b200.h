@@ -166,6 +166,9 @@ int qr_stats(qr_handle* h, double* out16, int reset_after, void* stream);
 int64_t qr_launch_count(void);
 const char* qr_last_error(void);
 int qr_abi_version(void);
+/* Row stride, in floats, of the obs and final_obs buffers of qr_get_buffers (= obs_dim unless the library was built
+ * with padded observation rows). */
+int qr_obs_stride(const qr_handle* h);
 
 #ifdef __cplusplus
 }

@@ -149,3 +149,6 @@ extern "C" void tw_actor(int mode, const float* obs, float* act)
     if (mode == 1) actor_td3_mono(obs, act);
     else { actor_td3_modul1(obs, act); actor_td3_modul2(obs + 15, act + 4); }
 }
+
+// row stride of the obs / final_obs arrays this build of the kernels expects (QR_OBS_PAD experiment)
+extern "C" int tw_obs_stride(int mode) { return obs_stride_of(mode == 1 ? 23 : 18); }

@@ -81,7 +81,9 @@ class HostEnv:
         self.state = np.zeros((18, n), T); self.state[6] = 1; self.state[10] = 1; self.state[14] = 1
         self.integ = np.zeros((8, n), T); self.params = np.zeros((6, n), T); self.goal = np.zeros((12, n), T); self.goal[6] = 1
         self.traj = np.zeros((12, n), T)
-        self.obs = np.zeros((n, self.O), np.float32); self.final_obs = np.zeros((n, self.O), np.float32)
+        S = int(K.tw_obs_stride(int(cfg.mode)))        # = O unless the twin was built with QR_OBS_PAD
+        self._obs_base = np.zeros((n, S), np.float32); self._final_obs_base = np.zeros((n, S), np.float32)
+        self.obs = self._obs_base[:, :self.O]; self.final_obs = self._final_obs_base[:, :self.O]
         self.reward = np.zeros((n, self.G), T); self.done = np.zeros((n, self.G), np.uint8)
         self.terminated = np.zeros(n, np.uint8); self.truncated = np.zeros(n, np.uint8)
         self.nfev = np.zeros(n, np.int32); self.status = np.zeros(n, np.uint8)
