@@ -35,7 +35,8 @@ def build(force=False, verbose=False, out=None, defines=()):
     """out / defines: build an experimental variant next to the product library (tools/ab_build.py)."""
     if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + SOURCES
+    extra = os.environ.get("QR_NVCC_EXTRA", "").split() if out else []   # experiments only (tools/ab_build.py), never the product build
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
