@@ -83,6 +83,35 @@ def test_create_rejects_inconsistent_configs():
     assert rc == 1 and b"Euler" in msg
 
 
+def test_step_kernel_sass_budget():
+    """Static guard on the headline kernel (CoupledWrapper, float32, single-step launch, on-device goal): registers within
+    the 12-warps-per-SM budget, and no local-memory traffic creeping into the persistent loop -- round 1 lost ~8 % to
+    loop-carried values that a large out-of-line call pushed into local memory.  The only LDL/STL left
+    belong to the rare re-projection call sites (a 9-word matrix handed over by pointer) and to the callees."""
+    import re
+    import shutil
+    import subprocess
+    from gym_rotor_b200 import _native
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    _native.load()
+    name = "_ZN2qr6k_stepIfLi1ELb0ELb1ELb0EEEvNS_8StepArgsIT_EE"
+    res = subprocess.run(["cuobjdump", "-res-usage", _native.LIB_PATH], capture_output=True, text=True).stdout
+    m = re.search(re.escape(name) + r".*?\n\s*(REG:(\d+).*)", res, re.S)
+    assert m, "kernel not found in the library"
+    assert int(m.group(2)) <= 170, m.group(1)                 # 384 threads x 170 registers = one CTA per SM
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", name, _native.LIB_PATH], capture_output=True, text=True).stdout
+    lines = [l for l in sass.split("\n") if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
+    assert 5000 < len(lines) < 9000, len(lines)
+    local = [i for i, l in enumerate(lines) if re.search(r"\b(LDL|STL)\b", l)]
+    # the persistent loop is the first ~3 300 instructions (the out-of-line routines follow it)
+    in_loop = [i for i in local if i < 3300]
+    assert len(in_loop) <= 60, (len(in_loop), in_loop[:10])     # 5 re-projection call sites x 10 words today
+    for i in in_loop:                                            # ... and each of them sits next to a CALL
+        window = "".join(lines[max(0, i - 12):i + 12])
+        assert "CALL" in window, lines[i]
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under gym_rotor_b200/ may reference it."""
     pkg = os.path.join(ROOT, "gym_rotor_b200")
