@@ -377,8 +377,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const int64_t e_first = __shfl_sync(FULL, e, 0);
             const int k_first = __shfl_sync(FULL, k, 0);
             const bool same = __all_sync(FULL, e - lane == e_first && k == k_first);   // (no warp primitive behind a short-circuit)
-            const bool coop = !QR_OBS_PAD && finmask == FULL && same && (e_first & 3) == 0 &&
+#if QR_OBS_PAD
+            const bool coop = finmask == FULL && same && !a.obs_roll;   // padded rows are 16-byte aligned; dense rollout rows: per lane
+#else
+            const bool coop = finmask == FULL && same && (e_first & 3) == 0 &&
                               (!a.obs_roll || ((reinterpret_cast<uintptr_t>(a.obs_roll) + (size_t)(((int64_t)k * N + e_first) * O) * 4) & 15) == 0);
+#endif
             if (fin) {
                 float o[23];
                 st = ode.status; nf = ode.nfev; nproj = ode.nproj;
@@ -426,8 +430,14 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 obs2 = (a.obs_roll && (last || POLICY)) ? a.obs + e * OS : nullptr;   // POLICY: the actor reads a.obs at the next sub-step
                 if (coop) {
                     float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
+#if QR_OBS_PAD
+#pragma unroll
+                    for (int i = 0; i < OS / 4; ++i)
+                        reinterpret_cast<float4*>(tile + lane * OS)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], (4 * i + 3 < O) ? o[4 * i + 3] : 0.f);
+#else
 #pragma unroll
                     for (int i = 0; i < O; ++i) tile[lane * O + i] = o[i];
+#endif
                 } else {
 #if QR_OBS_PAD
                     {   // rows inside a.obs are 16-byte aligned and padded: vector stores; caller's rollout storage: scalar
@@ -495,9 +505,15 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             if (coop) {
                 __syncwarp();
                 const float4* tile4 = reinterpret_cast<const float4*>(ks);
+#if QR_OBS_PAD
+                constexpr int NV = 32 * OS / 4;   // float4 elements of the 32-row block (rows padded)
+                float4* g1 = reinterpret_cast<float4*>((last || POLICY) ? a.obs + e_first * OS : nullptr);
+                float4* g2 = nullptr;
+#else
                 constexpr int NV = 32 * O / 4;   // float4 elements of the 32-row block
                 float4* g1 = reinterpret_cast<float4*>(a.obs_roll ? a.obs_roll + ((int64_t)k * N + e_first) * O : ((last || POLICY) ? a.obs + e_first * O : nullptr));
                 float4* g2 = reinterpret_cast<float4*>((a.obs_roll && (last || POLICY)) ? a.obs + e_first * O : nullptr);
+#endif
 #pragma unroll
                 for (int it = 0; it < (NV + 31) / 32; ++it) {
                     const int q = it * 32 + lane;
