@@ -232,7 +232,7 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
     if (mode == 2) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            o[i] = (float)ex[i]; o[3 + i] = (float)eIxn[i]; o[6 + i] = (float)ev[i]; o[9 + i] = (float)b3[i];
+            o[i] = (float)ex[i]; o[3 + i] = (float)eIxn[i]; o[6 + i] = (float)ev[i]; o[9 + i] = own_reg((float)b3[i]);
             o[12 + i] = (float)A::add(A::mul(eW[0], b1[i]), A::mul(eW[1], b2[i]));
         }
         o[15] = (float)eb1n; o[16] = (float)eIb1n; o[17] = (float)eW[2];
@@ -242,7 +242,7 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
             o[i] = (float)ex[i]; o[3 + i] = (float)eIxn[i]; o[6 + i] = (float)ev[i]; o[20 + i] = (float)eW[i];
         }
 #pragma unroll
-        for (int i = 0; i < 9; ++i) o[9 + i] = (float)R[i];
+        for (int i = 0; i < 9; ++i) o[9 + i] = own_reg((float)R[i]);
         o[18] = (float)eb1n; o[19] = (float)eIb1n;
     }
     return fl;

@@ -14,27 +14,10 @@
 #include "qr_traj.cuh"
 #include "generated/actor_td3.cuh"
 
-// experimental (off: not measured yet): claim the next 32-env tile one acquisition ahead, so that the L2 round trip
-// of the tile counter's atomic (2.9 % of the stall samples in capture r01u) overlaps a whole round of work
-#ifndef QR_TILE_PREFETCH
-#define QR_TILE_PREFETCH 0
-#endif
-// experimental (off: not measured yet): write the per-lane observation rows and the released state with streaming
-// stores (st.global.cs): the data is not read again by this launch
-#ifndef QR_STREAM_STORES
-#define QR_STREAM_STORES 0
-#endif
-// experimental (off: not measured yet): fetch the next env's state with streaming loads (ld.global.cs)
-#ifndef QR_STREAM_LOADS
-#define QR_STREAM_LOADS 0
-#endif
-// experimental (off: not measured yet): rows of the obs / final_obs buffers padded to a multiple of 4 floats (23 -> 24,
-// 18 -> 20), so that a lane writes its row as 16-byte vectors instead of 23 scattered 4-byte stores.  qr_obs_stride()
-// reports the row stride to the host side; rollout storage handed in by the caller stays dense.
-#ifndef QR_OBS_PAD
-#define QR_OBS_PAD 0
-#endif
-__host__ __device__ constexpr int obs_stride_of(int O) { return QR_OBS_PAD ? ((O + 3) & ~3) : O; }
+// Rows of the obs / final_obs buffers are padded to a multiple of 4 floats (23 -> 24, 18 -> 20), so that a lane writes its row as
+// 16-byte vectors instead of scattered 4-byte stores (measured +13 %, profiles/r02a_ab.txt).  qr_obs_stride() reports the row
+// stride to the host side; rollout storage handed in by the caller stays dense.
+__host__ __device__ constexpr int obs_stride_of(int O) { return (O + 3) & ~3; }
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
@@ -256,10 +239,6 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     int64_t tile_base = 0;    // warp-uniform: first env of the tile currently being handed out
     int tile_pos = 32;        // warp-uniform: envs of that tile already taken (32 = none left)
     bool exhausted = false;   // warp-uniform: the counter ran past the last tile
-#if QR_TILE_PREFETCH
-    unsigned long long pend = ~0ULL;   // lane 0: tile claimed ahead of need (~0 = none)
-    const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
-#endif
 
     // per-lane persistent state (registers).  Everything that is only needed when a step ENDS -- integral
     // errors, the goal of the step in flight, episode return / length / index -- lives in the lane's stash in
@@ -302,16 +281,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 int64_t base2 = -1;
                 if (cnt > rem && !exhausted) {
                     unsigned long long t = 0;
-#if QR_TILE_PREFETCH
-                    if (lane == 0) {
-                        t = (pend != ~0ULL) ? pend : atomicAdd(a.tile_counter, 1ULL);
-                        // not in the last wave of the launch: a claimed tile is bound to this warp, which would
-                        // lengthen the tail of the persistent grid
-                        pend = (t + total_warps < (unsigned long long)ntiles) ? atomicAdd(a.tile_counter, 1ULL) : ~0ULL;
-                    }
-#else
                     if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
-#endif
                     t = __shfl_sync(FULL, t, 0);
                     if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
                     else exhausted = true;
@@ -326,17 +296,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (ee < a.env_hi) {
                     has_next = true; e_next = ee;
                     // K0 and d are dead for a lane that is idle or has finished its step (A1 only reads ode's counters)
-#if QR_STREAM_LOADS
-                    d.fm = __ldcs(a.state + 0 * N + ee); d.g = __ldcs(a.state + 1 * N + ee); d.Mi0 = __ldcs(a.state + 2 * N + ee);
-#pragma unroll
-                    for (int i = 0; i < 14; ++i) K0[i] = __ldcs(a.state + (3 + i) * N + ee);
-                    d.Mi1 = __ldcs(a.state + 17 * N + ee);
-#else
+                    // (K0 is kept in the integrator's internal order, qr_dop853.cuh: the fetched state lands in the
+                    //  matching positions, so that y and K0 agree on which components form a register pair)
                     d.fm = a.state[0 * N + ee]; d.g = a.state[1 * N + ee]; d.Mi0 = a.state[2 * N + ee];
 #pragma unroll
-                    for (int i = 0; i < 14; ++i) K0[i] = a.state[(3 + i) * N + ee];
+                    for (int i = 0; i < 14; ++i) K0[zof(i)] = a.state[(3 + i) * N + ee];
                     d.Mi1 = a.state[17 * N + ee];
-#endif
                     if (a.actions) {
                         if (a.act_f32) {
                             const float* p = (const float*)a.actions + ee * A;
@@ -377,12 +342,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const int64_t e_first = __shfl_sync(FULL, e, 0);
             const int k_first = __shfl_sync(FULL, k, 0);
             const bool same = __all_sync(FULL, e - lane == e_first && k == k_first);   // (no warp primitive behind a short-circuit)
-#if QR_OBS_PAD
             const bool coop = finmask == FULL && same && !a.obs_roll;   // padded rows are 16-byte aligned; dense rollout rows: per lane
-#else
-            const bool coop = finmask == FULL && same && (e_first & 3) == 0 &&
-                              (!a.obs_roll || ((reinterpret_cast<uintptr_t>(a.obs_roll) + (size_t)(((int64_t)k * N + e_first) * O) * 4) & 15) == 0);
-#endif
             if (fin) {
                 float o[23];
                 st = ode.status; nf = ode.nfev; nproj = ode.nproj;
@@ -430,16 +390,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 obs2 = (a.obs_roll && (last || POLICY)) ? a.obs + e * OS : nullptr;   // POLICY: the actor reads a.obs at the next sub-step
                 if (coop) {
                     float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
-#if QR_OBS_PAD
 #pragma unroll
                     for (int i = 0; i < OS / 4; ++i)
                         reinterpret_cast<float4*>(tile + lane * OS)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], (4 * i + 3 < O) ? o[4 * i + 3] : 0.f);
-#else
-#pragma unroll
-                    for (int i = 0; i < O; ++i) tile[lane * O + i] = o[i];
-#endif
                 } else {
-#if QR_OBS_PAD
                     {   // rows inside a.obs are 16-byte aligned and padded: vector stores; caller's rollout storage: scalar
                         float op[OS];
 #pragma unroll
@@ -459,21 +413,6 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                             }
                         }
                     }
-#else
-                    if (obs1) {
-#if QR_STREAM_STORES
-#pragma unroll
-                        for (int i = 0; i < O; ++i) { if (!POLICY) __stcs(obs1 + i, o[i]); else obs1[i] = o[i]; }
-#else
-#pragma unroll
-                        for (int i = 0; i < O; ++i) obs1[i] = o[i];
-#endif
-                    }
-                    if (obs2) {
-#pragma unroll
-                        for (int i = 0; i < O; ++i) obs2[i] = o[i];
-                    }
-#endif
                 }
                 rew0f = (float)rew[0];
                 ep_ret0 += (T)rew[0];
@@ -505,15 +444,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             if (coop) {
                 __syncwarp();
                 const float4* tile4 = reinterpret_cast<const float4*>(ks);
-#if QR_OBS_PAD
                 constexpr int NV = 32 * OS / 4;   // float4 elements of the 32-row block (rows padded)
                 float4* g1 = reinterpret_cast<float4*>((last || POLICY) ? a.obs + e_first * OS : nullptr);
                 float4* g2 = nullptr;
-#else
-                constexpr int NV = 32 * O / 4;   // float4 elements of the 32-row block
-                float4* g1 = reinterpret_cast<float4*>(a.obs_roll ? a.obs_roll + ((int64_t)k * N + e_first) * O : ((last || POLICY) ? a.obs + e_first * O : nullptr));
-                float4* g2 = reinterpret_cast<float4*>((a.obs_roll && (last || POLICY)) ? a.obs + e_first * O : nullptr);
-#endif
 #pragma unroll
                 for (int it = 0; it < (NV + 31) / 32; ++it) {
                     const int q = it * 32 + lane;
@@ -581,21 +514,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     // release the env: state back to HBM (not the terminal state of an env whose reset is queued)
                     if (!deferred) {
 #pragma unroll
-#if QR_STREAM_STORES
-                        for (int i = 0; i < 3; ++i) __stcs(a.state + i * N + e, x[i]);
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) __stcs(a.state + (3 + i) * N + e, y[i]);
-                        __stcs(a.state + 15 * N + e, y[12]); __stcs(a.state + 16 * N + e, y[13]); __stcs(a.state + 17 * N + e, W3);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) __stcs(a.integ + i * N + e, In[i]);
-#else
                         for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
 #pragma unroll
                         for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
                         a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) a.integ[i * N + e] = In[i];
-#endif
                     }
                     a.ep_return[e] = ep_ret0;
                     if (G == 2) a.ep_return[N + e] = ep_ret1;
@@ -611,7 +535,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             e = e_next; k = 0; busy = true; need_init = true;
             x[0] = d.fm; x[1] = d.g; x[2] = d.Mi0; W3 = d.Mi1;
 #pragma unroll
-            for (int i = 0; i < 14; ++i) y[i] = K0[i];
+            for (int i = 0; i < 14; ++i) y[i] = K0[zof(i)];
             // end-of-step values go global -> stash without passing through registers (needed when the step ends)
 #pragma unroll
             for (int i = 0; i < 8; ++i) cp_async<sizeof(T)>(sh + (S_I + i) * 32, a.integ + i * N + e);
@@ -662,9 +586,6 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 QR_PKI(50) = (int32_t)(uint32_t)e_next; QR_PKI(51) = (int32_t)(e_next >> 32);
                 QR_PKI(52) = (int32_t)(uint32_t)tile_base; QR_PKI(53) = (int32_t)(tile_base >> 32);
                 QR_PKI(54) = tile_pos; QR_PKI(55) = rq_n;
-#if QR_TILE_PREFETCH
-                QR_PKI(56) = (int32_t)(uint32_t)pend; QR_PKI(57) = (int32_t)(pend >> 32);
-#endif
                 if (do_reset) {
                     float dummy[23];
                     // the new episode's first observation replaces the terminal one in the step's output row
@@ -687,9 +608,6 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 e_next = (int64_t)(((uint64_t)(uint32_t)QR_PKI(51) << 32) | (uint32_t)QR_PKI(50));
                 tile_base = (int64_t)(((uint64_t)(uint32_t)QR_PKI(53) << 32) | (uint32_t)QR_PKI(52));
                 tile_pos = QR_PKI(54); rq_n = QR_PKI(55);
-#if QR_TILE_PREFETCH
-                pend = ((unsigned long long)(uint32_t)QR_PKI(57) << 32) | (uint32_t)QR_PKI(56);
-#endif
 #undef QR_PKI
                 if (do_reset) {
                     const T* sc = ks + lane * 32;   // what auto_reset_env left in this lane's scratch
@@ -852,6 +770,26 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const bool live = busy && !fin;
             const bool f2 = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, lane, live);
             if (live) fin = f2;
+            // rare: some stage matrix of the speculative attempt failed the SO(3) test -> the lane redoes the attempt out
+            // of line with the reference's per-stage re-projection.  The call works on copies, so that the loop's
+            // registers never have their address taken.
+            if (__any_sync(FULL, live && ode.checked != 0)) {
+                if (live && ode.checked != 0) {
+                    T tx[3], ty[14], tK[14], tW3 = W3;
+                    Dyn<T> td = d;
+                    OdeLane<T> to = ode;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) tx[i] = x[i];
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) { ty[i] = y[i]; tK[i] = K0[i]; }
+                    fin = dop853_attempt_checked<T>(tx, ty, &tW3, &td, c.dt, c.rtol, c.atol, tK, &to);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) x[i] = tx[i];
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) { y[i] = ty[i]; K0[i] = tK[i]; }
+                    W3 = tW3; ode = to;
+                }
+            }
         }
     }
 

@@ -19,6 +19,18 @@
 
 namespace qr {
 
+// A copy in a register of its own.  The observation row leaves the kernel as 16-byte vectors, whose registers must be
+// consecutive; entries that are plain copies of the attitude (float32 mode: no conversion in between) would otherwise
+// tie the persistent state to that grouping, which conflicts with the integrator's register pairs (qr_dop853.cuh) and
+// costs moves in every stage instead of once per step.
+#if QR_PTX
+QR_DEV float own_reg(float v) { float r; asm volatile("mov.b32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+QR_DEV double own_reg(double v) { double r; asm volatile("mov.b64 %0, %1;" : "=d"(r) : "d"(v)); return r; }
+#else
+QR_DEV float own_reg(float v) { return v; }
+QR_DEV double own_reg(double v) { return v; }
+#endif
+
 template <typename T> struct num;
 
 template <> struct num<float> {
@@ -223,7 +235,7 @@ template <typename T, bool NEWTON = false> QR_DEV int ensure_so3(T* R)
     for (int i = 0; i < 9; ++i) tmp[i] = R[i];
     int bad = project_so3<T>(tmp);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = tmp[i];
+    for (int i = 0; i < 9; ++i) R[i] = own_reg(tmp[i]);   // (rare path) no vector reload straight into the caller's registers
     return 1 | (bad << 1);
 }
 

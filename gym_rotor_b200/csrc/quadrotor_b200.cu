@@ -223,35 +223,6 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     QR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     QR_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     h->smem_optin -= 256;    // reserve
-    {
-        static bool tab_done[64] = {false};
-        if (!tab_done[device & 63]) {
-            qr::Tableau t64; qr::TableauF t32;
-            qr::fill_tableau(t64);
-            for (int i = 0; i < 12; ++i) {
-                for (int j = 0; j < 12; ++j) t32.A[i][j] = (float)t64.A[i][j];
-                t32.B[i] = (float)t64.B[i]; t32.E5[i] = (float)t64.E5[i]; t32.E3[i] = (float)t64.E3[i]; t32.C[i] = (float)t64.C[i];
-            }
-            {   // flattened couplings (qr_dop853.cuh: Tableau::P)
-                int np = 0;
-                for (int s = 0; s < 16; ++s) t64.Ps[s] = t32.Ps[s] = 0;
-                for (int s = 1; s <= 11; ++s) {
-                    t64.Ps[s] = t32.Ps[s] = np;
-                    for (int j = 1; j < s; ++j) {
-                        if (t64.A[s][j] == 0.0) continue;
-                        t64.P[np].c = t64.A[s][j]; t64.P[np].off = qr::k_slot_host(j) * qr::QR_SLOT_ELEMS * (int)sizeof(double);
-                        t32.P[np].c = (float)t64.A[s][j]; t32.P[np].off = qr::k_slot_host(j) * qr::QR_SLOT_ELEMS * (int)sizeof(float);
-                        ++np;
-                    }
-                }
-                for (int s = 12; s < 16; ++s) t64.Ps[s] = t32.Ps[s] = np;
-                for (int q = np; q < 48; ++q) { t64.P[q].c = 0; t64.P[q].off = 0; t32.P[q].c = 0; t32.P[q].off = 0; }
-            }
-            QR_CUDA(cudaMemcpyToSymbol(qr::c_tab64, &t64, sizeof(t64)));
-            QR_CUDA(cudaMemcpyToSymbol(qr::c_tab32, &t32, sizeof(t32)));
-            tab_done[device & 63] = true;
-        }
-    }
     // identity attitude, nominal parameters, b1d = e1: a defined state before the first reset
     {
         std::vector<double> st(18 * n, 0.0), par(6 * n), gl(12 * n, 0.0);

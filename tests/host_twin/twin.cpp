@@ -34,43 +34,11 @@ template <typename T> EnvConst<T> make_const(const qr_config& c)   // same assig
     return e;
 }
 
-bool g_tab_done = false;
-void fill_tables()   // as qr_create does for the device
-{
-    if (g_tab_done) return;
-    Tableau t64;
-    fill_tableau(t64);
-    int np = 0;
-    for (int s = 0; s < 16; ++s) t64.Ps[s] = 0;
-    for (int s = 1; s <= 11; ++s) {
-        t64.Ps[s] = np;
-        for (int j = 1; j < s; ++j) {
-            if (t64.A[s][j] == 0.0) continue;
-            t64.P[np].c = t64.A[s][j]; t64.P[np].off = k_slot_host(j) * QR_SLOT_ELEMS * (int)sizeof(double);
-            ++np;
-        }
-    }
-    for (int s = 12; s < 16; ++s) t64.Ps[s] = np;
-    for (int q = np; q < 48; ++q) { t64.P[q].c = 0; t64.P[q].off = 0; }
-    c_tab64 = t64;
-    TableauF t32;
-    for (int i = 0; i < 12; ++i) {
-        for (int j = 0; j < 12; ++j) t32.A[i][j] = (float)t64.A[i][j];
-        t32.B[i] = (float)t64.B[i]; t32.E5[i] = (float)t64.E5[i]; t32.E3[i] = (float)t64.E3[i]; t32.C[i] = (float)t64.C[i];
-    }
-    for (int s = 0; s < 16; ++s) t32.Ps[s] = t64.Ps[s];
-    for (int q = 0; q < 48; ++q) { t32.P[q].c = (float)t64.P[q].c; t32.P[q].off = t64.P[q].off / 2; }   // byte offsets of float slots
-    c_tab32 = t32;
-    g_tab_done = true;
-}
-
-
 template <typename T>
 int step_one(const qr_config* cfg, const double* state, const double* integ, const double* params, double* goal_io,
              const double* action, int act_is_f32, double* state_out, double* integ_out, float* obs_out, double* reward_out,
              int* done_out, int* nfev_out, int* nproj_out)
 {
-    fill_tables();
     const EnvConst<T> c = make_const<T>(*cfg);
     const int MODE = c.mode;
     const int O = (MODE == 1) ? 23 : 18;
@@ -130,7 +98,10 @@ int step_one(const qr_config* cfg, const double* state, const double* integ, con
     // ---- B
     static T ks[QR_NSLOTS * QR_SLOT_ELEMS];
     int guard = 0;
-    while (!fin && guard++ < 100000) fin = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, 0, true);
+    while (!fin && guard++ < 100000) {
+        fin = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, 0, true);
+        if (ode.checked) fin = dop853_attempt_checked<T>(x, y, &W3, &d, c.dt, c.rtol, c.atol, K0, &ode);   // as phase B of k_step
+    }
     // ---- A1
     for (int i = 0; i < 3; ++i) r.x[i] = x[i];
     for (int i = 0; i < 14; ++i) r.y[i] = y[i];

@@ -37,34 +37,6 @@ template <typename T> void fill_const(EnvConst<T>& e, const qr_config& c)   // a
     e.env_type = c.env_type; e.max_episode_steps = c.max_episode_steps; e.diagnostics = c.reserved0;
 }
 
-bool g_tab_done = false;
-void fill_tables()   // as qr_create does for the device
-{
-    if (g_tab_done) return;
-    Tableau t64; TableauF t32;
-    fill_tableau(t64);
-    int np = 0;
-    for (int s = 0; s < 16; ++s) t64.Ps[s] = 0;
-    for (int s = 1; s <= 11; ++s) {
-        t64.Ps[s] = np;
-        for (int j = 1; j < s; ++j) {
-            if (t64.A[s][j] == 0.0) continue;
-            t64.P[np].c = t64.A[s][j]; t64.P[np].off = k_slot_host(j) * QR_SLOT_ELEMS * (int)sizeof(double);
-            ++np;
-        }
-    }
-    for (int s = 12; s < 16; ++s) t64.Ps[s] = np;
-    for (int q = np; q < 48; ++q) { t64.P[q].c = 0; t64.P[q].off = 0; }
-    for (int i = 0; i < 12; ++i) {
-        for (int j = 0; j < 12; ++j) t32.A[i][j] = (float)t64.A[i][j];
-        t32.B[i] = (float)t64.B[i]; t32.E5[i] = (float)t64.E5[i]; t32.E3[i] = (float)t64.E3[i]; t32.C[i] = (float)t64.C[i];
-    }
-    for (int s = 0; s < 16; ++s) t32.Ps[s] = t64.Ps[s];
-    for (int q = 0; q < 48; ++q) { t32.P[q].c = (float)t64.P[q].c; t32.P[q].off = t64.P[q].off / 2; }
-    c_tab64 = t64; c_tab32 = t32;
-    g_tab_done = true;
-}
-
 template <typename T, int MODE, bool MULTI, bool GOAL1, bool POLICY = false> void lane_body(void* p) { k_step<T, MODE, MULTI, GOAL1, POLICY>(*(const StepArgs<T>*)p); }
 
 }  // namespace
@@ -80,7 +52,6 @@ struct tw_arrays {
 
 extern "C" int tw_kstep(const qr_config* cfg, const tw_arrays* b, int64_t env_lo, int64_t env_hi, int n_steps, int warps, int policy)
 {
-    fill_tables();
     unsigned long long tile_counter[2] = {0, 0};
     const bool multi = n_steps > 1 || policy, goal1 = cfg->goal_mode == QR_GOAL_TRAJ_MODE0;   // as launch_step()
     if (policy && cfg->mode == QR_MODE_QUAD) return -2;
@@ -121,7 +92,6 @@ extern "C" int tw_kstep(const qr_config* cfg, const tw_arrays* b, int64_t env_lo
 // k_norm_error_state (3), run thread by thread over [env_lo, env_hi).
 extern "C" int tw_companion(const qr_config* cfg, const tw_arrays* b, int which, const uint8_t* mask, int env_type)
 {
-    fill_tables();
     unsigned long long tile_counter[2] = {0, 0};
     const int64_t env_lo = 0, env_hi = cfg->n_envs;
     const int n_steps = 1;
@@ -150,5 +120,5 @@ extern "C" void tw_actor(int mode, const float* obs, float* act)
     else { actor_td3_modul1(obs, act); actor_td3_modul2(obs + 15, act + 4); }
 }
 
-// row stride of the obs / final_obs arrays this build of the kernels expects (QR_OBS_PAD experiment)
+// row stride of the obs / final_obs arrays this build of the kernels expects (rows are padded to a multiple of 4 floats)
 extern "C" int tw_obs_stride(int mode) { return obs_stride_of(mode == 1 ? 23 : 18); }

@@ -44,7 +44,7 @@ def _build(src, tmp, name, opt="-O1", defines=()):
 @pytest.fixture(scope="module")
 def libs(tmp_path_factory):
     tmp = str(tmp_path_factory.mktemp("twink"))
-    # QR_TWIN_DEFINES="QR_E3_FROM_B=1,QR_TILE_PREFETCH=1": run the whole file against an experimental kernel variant
+    # QR_TWIN_DEFINES="NAME=1,...": run the whole file against a kernel variant built with extra macros
     extra = tuple(d for d in os.environ.get("QR_TWIN_DEFINES", "").split(",") if d)
     K = _build("twin_kernel.cpp", tmp, "libtwink.so", defines=extra)
     K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
@@ -81,7 +81,7 @@ class HostEnv:
         self.state = np.zeros((18, n), T); self.state[6] = 1; self.state[10] = 1; self.state[14] = 1
         self.integ = np.zeros((8, n), T); self.params = np.zeros((6, n), T); self.goal = np.zeros((12, n), T); self.goal[6] = 1
         self.traj = np.zeros((12, n), T)
-        S = int(K.tw_obs_stride(int(cfg.mode)))        # = O unless the twin was built with QR_OBS_PAD
+        S = int(K.tw_obs_stride(int(cfg.mode)))        # padded row stride (obs_stride_of)
         self._obs_base = np.zeros((n, S), np.float32); self._final_obs_base = np.zeros((n, S), np.float32)
         self.obs = self._obs_base[:, :self.O]; self.final_obs = self._final_obs_base[:, :self.O]
         self.reward = np.zeros((n, self.G), T); self.done = np.zeros((n, self.G), np.uint8)
@@ -403,30 +403,6 @@ def test_kernel_fused_policy_rollout_flies_the_reference_eval_episode(libs, fw, 
     assert np.array_equal(a2.state, b2.state) and np.array_equal(a2.obs, b2.obs) and np.array_equal(a2.integ, b2.integ)
 
 
-def test_kernel_experimental_tile_prefetch_is_equivalent(libs, tmp_path):
-    """QR_TILE_PREFETCH (compile-time experiment, off in the product build): claiming the next tile one acquisition
-    ahead must not lose, duplicate or reorder work -- same outputs as the default build on a many-tile launch."""
-    outs = []
-    for defs in ((), ("QR_TILE_PREFETCH=1",)):
-        if defs:
-            K = _build("twin_kernel.cpp", str(tmp_path), "libtwink_pre.so", defines=defs)
-            K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
-        else:
-            K = libs[0]
-        g = np.load(os.path.join(G, "step_mono_a64.npz"))
-        n = g["action"].shape[0]
-        env = HostEnv(K, _config(1, n_envs=n, autoreset=1, max_episode_steps=3), warps=4)
-        env.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
-        env.ep_index[:] = 1
-        rng = np.random.default_rng(1)
-        for t in range(4):
-            env.launch(rng.uniform(-1, 1, (n, 4)))
-        outs.append((env.state.copy(), env.obs.copy(), env.ep_index.copy(), env.stats.copy()))
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b)
-    assert outs[0][3][7] == 4 * 1200 and outs[0][3][0] >= 1200
-
-
 def test_kernel_modul_quad_rollouts_and_external_goals(libs):
     """DecoupledWrapper and Quad-v0 through multi-step launches with EXTERNAL goals (the goal is read from the goal
     buffer at the end of every step) == single-step launches; float32; auto reset off and on."""
@@ -478,25 +454,6 @@ def test_kernel_edge_cases(libs):
     for m in (1, 5):
         tiny = HostEnv(K, _config(1, n_envs=m), warps=1); tiny.set_state(st[:m], ig[:m], par[:m], goal[:m]); tiny.launch(act[:m])
         assert np.array_equal(tiny.state, ref.state[:, :m]) and np.array_equal(tiny.obs, ref.obs[:m])
-
-
-def test_kernel_experimental_e3_from_b_keeps_parity(libs, tmp_path):
-    """QR_E3_FROM_B (compile-time experiment, off in the product build): forming the third-order error sums from the
-    B-weighted sums plus three correction terms changes rounding only -- the golden parity bars still hold."""
-    K = _build("twin_kernel.cpp", str(tmp_path), "libtwink_e3.so", defines=("QR_E3_FROM_B=1",))
-    K.tw_kstep.argtypes = [C.c_void_p, C.POINTER(TwArrays), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
-    for fw, tag, mode in (("MONO", "mono", 1), ("MODUL", "modul", 2)):
-        g = np.load(os.path.join(G, "step_%s_a64.npz" % tag))
-        n = g["action"].shape[0]
-        env = HostEnv(K, _config(mode, n_envs=n))
-        env.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
-        env.launch(np.ascontiguousarray(g["action"], np.float64))
-        assert _relerr(env.state.T, g["state_out"]) <= 1e-12 and (env.nfev == g["nfev"]).all()
-        assert int((env.obs.view(np.uint32) != g["obs"].view(np.uint32)).sum()) <= 3
-        e32 = HostEnv(K, _config(mode, dtype64=False, n_envs=n), warps=12)
-        e32.set_state(g["state_in"], g["integ_in"], g["params"], g["goal"])
-        e32.launch(g["action"].astype(np.float32))
-        assert np.abs(e32.state.T - g["state_out"]).max() <= 1e-5 and ((e32.nfev - 2) // 12 != (g["nfev"] - 2) // 12).mean() <= 0.03
 
 
 def test_kernel_fp64_free_running_vs_c_oracle(libs):

@@ -55,29 +55,7 @@ int main()
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    {   // tableau, as qr_create fills it
-        Tableau t64; TableauF t32;
-        fill_tableau(t64);
-        int np = 0;
-        for (int s = 0; s < 16; ++s) t64.Ps[s] = 0;
-        for (int s = 1; s <= 11; ++s) {
-            t64.Ps[s] = np;
-            for (int j = 1; j < s; ++j) {
-                if (t64.A[s][j] == 0.0) continue;
-                t64.P[np].c = t64.A[s][j]; t64.P[np].off = k_slot_host(j) * QR_SLOT_ELEMS * (int)sizeof(double); ++np;
-            }
-        }
-        for (int s = 12; s < 16; ++s) t64.Ps[s] = np;
-        for (int q = np; q < 48; ++q) { t64.P[q].c = 0; t64.P[q].off = 0; }
-        for (int i = 0; i < 12; ++i) {
-            for (int j = 0; j < 12; ++j) t32.A[i][j] = (float)t64.A[i][j];
-            t32.B[i] = (float)t64.B[i]; t32.E5[i] = (float)t64.E5[i]; t32.E3[i] = (float)t64.E3[i]; t32.C[i] = (float)t64.C[i];
-        }
-        for (int s = 0; s < 16; ++s) t32.Ps[s] = t64.Ps[s];
-        for (int q = 0; q < 48; ++q) { t32.P[q].c = (float)t64.P[q].c; t32.P[q].off = t64.P[q].off / 2; }
-        CK(cudaMemcpyToSymbol(c_tab64, &t64, sizeof(t64)));
-        CK(cudaMemcpyToSymbol(c_tab32, &t32, sizeof(t32)));
-    }
+
     const int threads = 384, iters = 64;
     const int64_t n = (int64_t)sms * threads;
     std::vector<float> h(n * 24, 0.f);
