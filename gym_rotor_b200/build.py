@@ -1,7 +1,10 @@
 """Builds the sm_100a shared library in-tree (gym_rotor_b200/csrc/libquadrotor_b200.so).
 
-nvcc cross-compiles without a GPU.  The library has no torch dependency: plain nvcc -shared.
+nvcc cross-compiles without a GPU.  The library has no torch dependency: plain nvcc, objects compiled in parallel
+(the step kernel's instantiations are spread over ten translation units, csrc/qr_step_tu.cu), then one link.
 """
+import concurrent.futures
+import hashlib
 import os
 import subprocess
 import sys
@@ -9,12 +12,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libquadrotor_b200.so")
-SOURCES = ["quadrotor_b200.cu"]
-DEPS = ["quadrotor_b200.cu", "qr_kernels.cuh", "qr_env.cuh", "qr_traj.cuh", "qr_dop853.cuh", "qr_math.cuh", "dop853_tableau.h",
+OBJ_DIR = os.path.join(CSRC, "_build")
+DEPS = ["quadrotor_b200.cu", "qr_step_tu.cu", "qr_kernels.cuh", "qr_env.cuh", "qr_traj.cuh", "qr_dop853.cuh", "qr_math.cuh", "dop853_tableau.h",
         os.path.join("generated", "actor_td3.cuh"),
         os.path.join("..", "..", "include", "quadrotor_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+# (object name, source, defines): the C ABI + companion kernels, then the step kernel per (dtype, mode, policy)
+UNITS = [("abi", "quadrotor_b200.cu", [])] + [
+    ("step_%s_m%d_p%d" % (t, m, p), "qr_step_tu.cu", ["QR_TU_T=%s" % t, "QR_TU_MODE=%d" % m, "QR_TU_POLICY=%d" % p])
+    for t in ("float", "double") for (m, p) in ((1, 0), (2, 0), (0, 0), (1, 1), (2, 1))]
 
 
 def _nvcc():
@@ -31,20 +37,47 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False, out=None, defines=()):
-    """out / defines: build an experimental variant next to the product library (tools/ab_build.py)."""
+def _compile(args):
+    cmd, name = args
+    res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return name, res.returncode, res.stdout
+
+
+def build(force=False, verbose=False, out=None, defines=(), only=None):
+    """out / defines: build an experimental variant next to the product library (tools/ab_build.py).
+    only: substrings of unit names to recompile (development; the other objects must exist already)."""
     if out is None and not force and not needs_build():
         return LIB
     extra = os.environ.get("QR_NVCC_EXTRA", "").split() if out else []   # experiments only (tools/ab_build.py), never the product build
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    tag = hashlib.sha1((" ".join(sorted(defines)) + "|" + " ".join(extra)).encode()).hexdigest()[:10] if (defines or extra) else "product"
+    odir = os.path.join(OBJ_DIR, tag)
+    os.makedirs(odir, exist_ok=True)
+    jobs, objs = [], []
+    for name, src, defs in UNITS:
+        obj = os.path.join(odir, name + ".o")
+        objs.append(obj)
+        if only is not None and os.path.exists(obj) and not any(o in name for o in only):
+            continue
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-D" + d for d in list(defs) + list(defines)] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        jobs.append((cmd, name))
+    workers = max(1, min(len(jobs), os.cpu_count() or 4))
+    failed = False
+    with concurrent.futures.ThreadPoolExecutor(workers) as ex:
+        for name, rc, log in ex.map(_compile, jobs):
+            if rc != 0:
+                sys.stderr.write("---- %s\n%s" % (name, log))
+                failed = True
+            elif verbose:
+                print("---- %s\n%s" % (name, log))
+    if failed:
+        raise RuntimeError("nvcc failed building %s" % (out or LIB))
+    res = subprocess.run([_nvcc(), "-shared", "-o", out or LIB] + objs, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
-        raise RuntimeError("nvcc failed building %s" % LIB)
-    if verbose:
-        print(res.stdout)
-    return LIB
+        raise RuntimeError("link failed for %s" % (out or LIB))
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    print(build(force="--force" in sys.argv or bool(only), verbose="-v" in sys.argv, only=only or None))

@@ -939,4 +939,22 @@ template <typename T> __global__ void k_soa_to_aos(const T* soa, double* aos, in
     aos[i] = (double)soa[(int64_t)c * n + e];
 }
 
+// ---- the step kernel's instantiations live in their own translation units (qr_step_tu.cu, compiled in parallel) ----
+template <typename T> using step_kernel_t = void (*)(const StepArgs<T>);
+#define QR_DECL_STEP(T, M, P) step_kernel_t<T> step_kernel_##T##_m##M##_p##P(bool multi, bool goal1);
+QR_DECL_STEP(float, 0, 0) QR_DECL_STEP(float, 1, 0) QR_DECL_STEP(float, 2, 0) QR_DECL_STEP(float, 1, 1) QR_DECL_STEP(float, 2, 1)
+QR_DECL_STEP(double, 0, 0) QR_DECL_STEP(double, 1, 0) QR_DECL_STEP(double, 2, 0) QR_DECL_STEP(double, 1, 1) QR_DECL_STEP(double, 2, 1)
+#undef QR_DECL_STEP
+template <typename T> inline step_kernel_t<T> step_kernel(int mode, bool multi, bool goal1, bool policy);
+template <> inline step_kernel_t<float> step_kernel<float>(int mode, bool multi, bool goal1, bool policy)
+{
+    if (policy) return mode == 1 ? step_kernel_float_m1_p1(multi, goal1) : step_kernel_float_m2_p1(multi, goal1);
+    return mode == 1 ? step_kernel_float_m1_p0(multi, goal1) : mode == 2 ? step_kernel_float_m2_p0(multi, goal1) : step_kernel_float_m0_p0(multi, goal1);
+}
+template <> inline step_kernel_t<double> step_kernel<double>(int mode, bool multi, bool goal1, bool policy)
+{
+    if (policy) return mode == 1 ? step_kernel_double_m1_p1(multi, goal1) : step_kernel_double_m2_p1(multi, goal1);
+    return mode == 1 ? step_kernel_double_m1_p0(multi, goal1) : mode == 2 ? step_kernel_double_m2_p0(multi, goal1) : step_kernel_double_m0_p0(multi, goal1);
+}
+
 }  // namespace qr

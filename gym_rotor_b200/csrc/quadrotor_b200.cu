@@ -113,19 +113,8 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     // launches (the env keeps stepping in its lane) reset inside the step kernel
     const bool multi = n_steps > 1 || policy;   // the policy variants exist for the in-kernel reset flavour only
     const bool goal1 = h->cfg.goal_mode == QR_GOAL_TRAJ_MODE0;   // only with a wrapper mode (checked in qr_create)
-    void (*kern)(const qr::StepArgs<T>);
-    if (policy && h->cfg.mode == QR_MODE_COUPLED)
-        kern = goal1 ? qr::k_step<T, 1, true, true, true> : qr::k_step<T, 1, true, false, true>;
-    else if (policy && h->cfg.mode == QR_MODE_DECOUPLED)
-        kern = goal1 ? qr::k_step<T, 2, true, true, true> : qr::k_step<T, 2, true, false, true>;
-    else if (h->cfg.mode == QR_MODE_COUPLED)
-        kern = multi ? (goal1 ? qr::k_step<T, 1, true, true> : qr::k_step<T, 1, true, false>)
-                     : (goal1 ? qr::k_step<T, 1, false, true> : qr::k_step<T, 1, false, false>);
-    else if (h->cfg.mode == QR_MODE_DECOUPLED)
-        kern = multi ? (goal1 ? qr::k_step<T, 2, true, true> : qr::k_step<T, 2, true, false>)
-                     : (goal1 ? qr::k_step<T, 2, false, true> : qr::k_step<T, 2, false, false>);
-    else
-        kern = multi ? qr::k_step<T, 0, true, false> : qr::k_step<T, 0, false, false>;
+    // the kernel for this configuration (compiled in its own translation unit, qr_step_tu.cu)
+    const qr::step_kernel_t<T> kern = qr::step_kernel<T>(h->cfg.mode, multi, goal1, policy && h->cfg.mode != QR_MODE_QUAD);
     const int attr_idx = (policy ? 8 : 0) + (sizeof(T) == 8 ? 4 : 0) + (multi ? 2 : 0) + (goal1 ? 1 : 0);
     if (!h->attr_set[attr_idx]) {
         QR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->smem_optin / per_warp * per_warp)));
