@@ -58,7 +58,11 @@ def build(force=False, verbose=False, out=None, defines=(), only=None):
         objs.append(obj)
         if only is not None and os.path.exists(obj) and not any(o in name for o in only):
             continue
-        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-D" + d for d in list(defs) + list(defines)] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        # a wrapper source per unit, so that every cubin in the library has its own name (cuobjdump -xelf, tools/*.py)
+        wrap = os.path.join(odir, name + ".cu")
+        with open(wrap, "w") as f:
+            f.write('#include "%s"\n' % os.path.join(CSRC, src))
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I" + CSRC] + ["-D" + d for d in list(defs) + list(defines)] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, wrap]
         jobs.append((cmd, name))
     workers = max(1, min(len(jobs), os.cpu_count() or 4))
     failed = False
@@ -71,7 +75,7 @@ def build(force=False, verbose=False, out=None, defines=(), only=None):
                 print("---- %s\n%s" % (name, log))
     if failed:
         raise RuntimeError("nvcc failed building %s" % (out or LIB))
-    res = subprocess.run([_nvcc(), "-shared", "-o", out or LIB] + objs, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out or LIB] + objs, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
         raise RuntimeError("link failed for %s" % (out or LIB))

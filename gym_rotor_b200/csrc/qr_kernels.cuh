@@ -21,6 +21,9 @@ __host__ __device__ constexpr int obs_stride_of(int O) { return (O + 3) & ~3; }
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
+#ifndef QR_KS_SLOTS_F32
+#define QR_KS_SLOTS_F32 6   // float32 keeps K2..K8 in slots 0..5 (qr_dop853.cuh); with 6 the block fits the 196 KB shared-memory configuration (60 KB of L1 instead of 28: +5 %, profiles/r02/r02e_ab.txt)
+#endif
 namespace qr {
 
 constexpr int QR_BLOCK = 128;        // companion kernels (reset, goal init, observation)
@@ -195,13 +198,23 @@ QR_DEV float warp_sum_f(float v)
 // Per-warp shared memory: KS[8][14][32] T (stage derivatives) | STASH[36][32] T (per-lane values that are only needed
 //                         when a step ends: integrals, goal, episode counters; and the landing zone of the next
 //                         env's action / parameters / goal, fetched ahead) | WS[16] f64 (statistics) |
-//                         RQ[64] i32 (single-step launches: envs whose reset is queued, see `parked reset`)
+//                         RQ[64] i32 (envs whose reset is queued, see `parked reset`).
+// Multi-step launches keep two more small arrays in the four unused stash slots (32..35): the sub-step at which a queued
+// env goes on (i16), and CQ[64] (env i32, step i16), the reset envs that wait for a free lane to go on stepping.
+// The float32 total is 16 512 bytes per warp: 12 warps (all the registers allow) + the 1 KB the system reserves fit the
+// 196 KB shared-memory configuration, which leaves 60 KB of L1 for the loop's few spilled values and the row stores; at
+// 19 328 bytes (228 KB configuration, 28 KB of L1) the kernel was 5 % slower, and beyond that it loses a warp per SM (-9 %).
 template <typename T> struct warp_smem {
-    static constexpr size_t ks_bytes = (size_t)QR_NSLOTS * QR_SLOT_ELEMS * sizeof(T);
+    static constexpr size_t park_elems = 1024 + 58 * 32;   // phase A's other use of the stage storage: reset scratch + parked lane state
+    static constexpr size_t slot_elems = (size_t)(sizeof(T) == 4 ? QR_KS_SLOTS_F32 : QR_NSLOTS) * QR_SLOT_ELEMS;
+    static constexpr size_t ks_bytes = (slot_elems > park_elems ? slot_elems : park_elems) * sizeof(T);
     static constexpr size_t os_bytes = 32 * 36 * sizeof(T);   // the stash: 36 slots per lane
     static constexpr size_t ws_bytes = 16 * sizeof(double);
-    static constexpr size_t rq_bytes = 64 * sizeof(int32_t);
+    static constexpr int rq_cap = 64, cq_cap = 64;   // envs out of their lane never exceed QR_RESET_BATCH - 1 + 32 (see `parked reset`)
+    static constexpr size_t rq_bytes = rq_cap * sizeof(int32_t);
     static constexpr size_t bytes = ks_bytes + os_bytes + ws_bytes + rq_bytes;   // multiple of 16
+    static_assert(sizeof(T) == 8 || bytes * 12 + 1024 <= 196 * 1024, "float32: 12 warps per SM within the 196 KB shared-memory configuration");
+    static_assert(4 * 32 * sizeof(T) >= cq_cap * 6 + rq_cap * 2, "the queues of multi-step launches live in stash slots 32..35");
 };
 
 // GOAL1: the goal is generated on the device in trajectory mode 0 (config goal_mode == 1) -- a template parameter so
@@ -222,11 +235,16 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const EnvConst<T>& c = a.c;
     const int64_t N = a.n;
+    const int NS = MULTI ? a.n_steps : 1;   // single-step kernels: the sub-step counter k folds to the constant 0
     unsigned char* wbase = smem_raw + warp * warp_smem<T>::bytes;
     T* ks = reinterpret_cast<T*>(wbase);
     T* const sh = reinterpret_cast<T*>(wbase + warp_smem<T>::ks_bytes) + lane;   // stash slot j of this lane: sh[j * 32]
     double* ws = reinterpret_cast<double*>(wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes);
     int32_t* rq = reinterpret_cast<int32_t*>(wbase + warp_smem<T>::ks_bytes + warp_smem<T>::os_bytes + warp_smem<T>::ws_bytes);
+    // multi-step launches: CQ (env, step) and the steps of RQ's entries, in stash slots 32..35
+    int32_t* const cq = reinterpret_cast<int32_t*>(reinterpret_cast<T*>(wbase + warp_smem<T>::ks_bytes) + 32 * 32);
+    int16_t* const cqk = reinterpret_cast<int16_t*>(cq + warp_smem<T>::cq_cap);
+    int16_t* const rqk = cqk + warp_smem<T>::cq_cap;
     const Philox ph{a.key0, a.key1};
 
     if (lane < 16) ws[lane] = 0.0;
@@ -252,7 +270,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     constexpr int S_I = 0, S_B1D = 8, S_WD = 11, S_RET0 = 14, S_LEN = 15, S_IDX = 16, S_RET1 = 17;   // stash slots: env in flight
     constexpr int S_ACT = 18, S_PAR = 23, S_NB1D = 29;   // next env, fetched ahead: action (<= 5), parameters (6), b1d (3)
     bool has_next = false;   // K0 / d hold the NEXT env's state (loads in flight), the stash its action etc.
+    bool fresh = false;      // the env was adopted in this round's A2: its action / parameters / b1d are in the stash
     int64_t e_next = 0;
+    int k_next = 0;          // multi-step launches: the sub-step at which the fetched env goes on (a reset env resumes mid-rollout)
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = 0;
 #pragma unroll
@@ -262,39 +282,48 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     ode.t = 0; ode.h_abs = c.dt; ode.rejected = 0; ode.nfev = 0; ode.status = 0; ode.nproj = 0; ode.checked = 0;
 
     int rq_n = 0;   // warp-uniform: entries in RQ
+    int cq_n = 0;   // warp-uniform: entries in CQ (multi-step launches)
 
     for (;;) {
         // =============================== phase A ===============================
         const unsigned finmask = __ballot_sync(FULL, fin);
-        bool rs_pending = false; int64_t rs_e = 0; uint32_t rs_ep = 0; float *rs_o1 = nullptr, *rs_o2 = nullptr;   // multi-step: this lane's env needs a reset
         // ---- A0: lanes that are idle, or about to release their env, are given the next env of the warp's sequence
         // NOW and start fetching it: the state into the (dead) registers of K0 and d, action / parameters / goal
         // into the stash with cp.async.  The round trip to HBM overlaps the end-of-step work below instead of
         // stalling the start of the next step.
         {
-            const bool leaving = fin && (k == a.n_steps - 1);
+            const bool leaving = fin && (k == NS - 1);
             const unsigned need = __ballot_sync(FULL, (!busy || leaving) && !has_next);
             const int cnt = __popc(need);
-            if (cnt && !(exhausted && tile_pos >= 32)) {
-                const int rank = __popc(need & ((1u << lane) - 1u));
-                const int rem = 32 - tile_pos;
-                int64_t base2 = -1;
-                if (cnt > rem && !exhausted) {
-                    unsigned long long t = 0;
-                    if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
-                    t = __shfl_sync(FULL, t, 0);
-                    if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
-                    else exhausted = true;
-                }
+            const int ncq = MULTI ? min(cnt, cq_n) : 0;   // reset envs waiting to go on stepping are served first
+            if (cnt && (ncq > 0 || !(exhausted && tile_pos >= 32))) {
+                const bool mine = (need >> lane) & 1u;
+                const int rank = __popc(need & ((1u << lane) - 1u)) - ncq;   // < 0: this lane takes a waiting env
                 int64_t ee = a.env_hi;
-                if ((need >> lane) & 1u) {
-                    if (rank < rem) ee = tile_base + tile_pos + rank;
-                    else if (base2 >= 0) ee = base2 + (rank - rem);
+                int kk = 0;
+                if (MULTI && mine && rank < 0) { ee = (int64_t)cq[cq_n + rank]; kk = cqk[cq_n + rank]; }
+                cq_n -= ncq;
+                const int cnt_t = cnt - ncq;   // lanes served from the tile sequence
+                if (cnt_t > 0 && !(exhausted && tile_pos >= 32)) {
+                    const int rem = 32 - tile_pos;
+                    int64_t base2 = -1;
+                    if (cnt_t > rem && !exhausted) {
+                        unsigned long long t = 0;
+                        if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
+                        t = __shfl_sync(FULL, t, 0);
+                        if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
+                        else exhausted = true;
+                    }
+                    if (mine && rank >= 0) {
+                        if (rank < rem) ee = tile_base + tile_pos + rank;
+                        else if (base2 >= 0) ee = base2 + (rank - rem);
+                    }
+                    if (cnt_t > rem) { tile_base = base2; tile_pos = (base2 >= 0) ? cnt_t - rem : 32; }
+                    else tile_pos += cnt_t;
                 }
-                if (cnt > rem) { tile_base = base2; tile_pos = (base2 >= 0) ? cnt - rem : 32; }
-                else tile_pos += cnt;
                 if (ee < a.env_hi) {
                     has_next = true; e_next = ee;
+                    if (MULTI) k_next = kk;
                     // K0 and d are dead for a lane that is idle or has finished its step (A1 only reads ode's counters)
                     // (K0 is kept in the integrator's internal order, qr_dop853.cuh: the fetched state lands in the
                     //  matching positions, so that y and K0 agree on which components form a register pair)
@@ -304,11 +333,11 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     d.Mi1 = a.state[17 * N + ee];
                     if (a.actions) {
                         if (a.act_f32) {
-                            const float* p = (const float*)a.actions + ee * A;
+                            const float* p = (const float*)a.actions + ((int64_t)kk * N + ee) * A;
 #pragma unroll
                             for (int i = 0; i < A; ++i) cp_async<4>(sh + (S_ACT + i) * 32, p + i);
                         } else if (sizeof(T) == 8) {
-                            const double* p = (const double*)a.actions + ee * A;
+                            const double* p = (const double*)a.actions + ((int64_t)kk * N + ee) * A;
 #pragma unroll
                             for (int i = 0; i < A; ++i) cp_async<8>(sh + (S_ACT + i) * 32, p + i);
                         }
@@ -328,7 +357,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         // ---- A1: finish the env.step that just completed ----
         if (finmask) {
             __syncwarp();   // phase B is over for every lane: the stage storage may be reused as reset scratch
-            bool ep_done = false, deferred = false, term = false, trunc = false;
+            bool ep_done = false, term = false, trunc = false;
             int nf = 0, st = 0, nproj = 0, ep_len_done = 0;
             float rew0f = 0.f;
             T ret_done0 = 0, ret_done1 = 0;
@@ -337,7 +366,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             int ep_len = 0;
             uint32_t ep_idx = 0;
             float *obs1 = nullptr, *obs2 = nullptr;   // where this step's observation row goes
-            const bool last = (k == a.n_steps - 1);
+            const bool last = (k == NS - 1);
             // all 32 lanes finish the same sub-step of 32 consecutive envs, first one 4-aligned (16-byte aligned rows block)
             const int64_t e_first = __shfl_sync(FULL, e, 0);
             const int k_first = __shfl_sync(FULL, k, 0);
@@ -462,13 +491,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             // queue the env (it leaves the lane anyway) so that a whole batch is reset at once. ----
             {
                 const unsigned wmask = __ballot_sync(FULL, ep_done);
-                if (wmask) {
-                    if (!MULTI) {   // RQ holds 64: at most QR_RESET_BATCH - 1 entries from earlier rounds + 32 new ones
-                        if (ep_done) { rq[rq_n + __popc(wmask & ((1u << lane) - 1u))] = (int32_t)e; deferred = true; }
-                        rq_n += __popc(wmask);
-                    } else if (ep_done) {
-                        rs_pending = true; rs_e = e; rs_ep = ep_idx; rs_o1 = obs1; rs_o2 = obs2;
+                if (wmask) {   // RQ holds 64: at most QR_RESET_BATCH - 1 entries from earlier rounds + 32 new ones
+                    if (ep_done) {
+                        const int q = rq_n + __popc(wmask & ((1u << lane) - 1u));
+                        rq[q] = (int32_t)e; if (MULTI) rqk[q] = (int16_t)(k + 1);   // the env goes on at sub-step k + 1 (multi-step launches)
                     }
+                    rq_n += __popc(wmask);
                 }
             }
             __syncwarp();
@@ -501,8 +529,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             }
             if (fin) {
                 fin = false;
-                k += 1;
-                if (k < a.n_steps) {
+                if (MULTI) k += 1;
+                if (MULTI && k < NS && !ep_done) {
                     need_init = true;   // the env stays in this lane: end-of-step values back into the stash
 #pragma unroll
                     for (int i = 0; i < 8; ++i) sh[(S_I + i) * 32] = In[i];
@@ -511,8 +539,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     stash_i32(sh, S_LEN) = ep_len;
                     stash_i32(sh, S_IDX) = (int32_t)ep_idx;
                 } else {
-                    // release the env: state back to HBM (not the terminal state of an env whose reset is queued)
-                    if (!deferred) {
+                    // release the env: state back to HBM -- but not the terminal state of an env whose reset is queued (the
+                    // reset writes the new one; in a multi-step launch another lane then goes on stepping it, see CQ)
+                    if (!ep_done) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
 #pragma unroll
@@ -532,7 +561,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         // ---- A2: idle lanes adopt the env fetched in A0 ----
         if (has_next && !busy) {
             has_next = false;
-            e = e_next; k = 0; busy = true; need_init = true;
+            e = e_next; k = MULTI ? k_next : 0; busy = true; need_init = true; if (MULTI) fresh = true;
             x[0] = d.fm; x[1] = d.g; x[2] = d.Mi0; W3 = d.Mi1;
 #pragma unroll
             for (int i = 0; i < 14; ++i) y[i] = K0[zof(i)];
@@ -549,22 +578,26 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         // ---- parked reset.  A reset is ~1 000 instructions and out of line; a call from inside this loop would put
         // every value that lives across it into local memory FOR THE WHOLE LOOP (measured: ~2.5 M local accesses per
         // launch, in-flight loads serialised behind them).  So the lane state is parked in the stage storage (free in
-        // phase A) around the call and re-defined from there afterwards: nothing is live across it.  Single-step
-        // launches reset a batch of queued envs, one per lane; multi-step launches the lanes' own envs. ----
+        // phase A) around the call and re-defined from there afterwards: nothing is live across it.  A whole
+        // batch of queued envs is reset at once, one per lane (the env left its lane when its episode ended).  In a
+        // multi-step launch a reset env that still has sub-steps to go then waits in CQ for the next free lane: a reset in
+        // the env's own lane -- one lane working, 31 waiting, in 40 % of the rounds -- cost 14 % of the launch. ----
         {
-            bool do_reset = false, r_cont = false;
+            bool do_reset = false;
             int64_t r_e = 0; uint32_t r_ep = 0; float *r_o1 = nullptr, *r_o2 = nullptr;
-            if (MULTI) {
-                do_reset = rs_pending; r_e = rs_e; r_ep = rs_ep; r_o1 = rs_o1; r_o2 = rs_o2;
-                r_cont = rs_pending && busy && e == rs_e;   // the env continues in this lane
-            } else if (rq_n >= QR_RESET_BATCH || (drained && rq_n > 0)) {
-                // at most 32 per pass; a burst (e.g. a common time limit) leaves the rest for the next round
+            int r_k = 0;   // the sub-step that ended the episode
+            if (rq_n >= QR_RESET_BATCH || (drained && rq_n > 0)) {
+                // at most 32 per pass; a burst (e.g. a common time limit) leaves the rest for the next round.  Neither queue can
+                // overflow: envs in flight (in a lane, in RQ or in CQ) only increase when a lane takes an env from the tile
+                // sequence, which it does only when CQ is empty, i.e. when they number at most 32 + QR_RESET_BATCH - 1.
                 const int n_now = min(rq_n, 32);
                 if (lane < n_now) {
                     do_reset = true; r_e = (int64_t)rq[rq_n - n_now + lane];
+                    if (MULTI) r_k = rqk[rq_n - n_now + lane] - 1;
+                    const bool r_last = r_k == NS - 1;
                     r_ep = __ldcg(a.ep_index + r_e);   // written when the env was released (already incremented)
-                    r_o1 = a.obs_roll ? a.obs_roll + r_e * O : a.obs + r_e * OS;
-                    r_o2 = a.obs_roll ? a.obs + r_e * OS : nullptr;
+                    r_o1 = a.obs_roll ? a.obs_roll + ((int64_t)r_k * N + r_e) * O : ((r_last || POLICY) ? a.obs + r_e * OS : nullptr);
+                    r_o2 = (a.obs_roll && (r_last || POLICY)) ? a.obs + r_e * OS : nullptr;
                 }
                 rq_n -= n_now;
             }
@@ -580,12 +613,13 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 pk[32 * 32] = d.fm; pk[33 * 32] = d.g; pk[34 * 32] = d.Mi0; pk[35 * 32] = d.Mi1; pk[36 * 32] = d.kw0; pk[37 * 32] = d.kw1; pk[38 * 32] = d.w3dot;
                 pk[39 * 32] = ode.t; pk[40 * 32] = ode.h_abs;
                 QR_PKI(41) = ode.rejected; QR_PKI(42) = ode.nfev; QR_PKI(43) = ode.status; QR_PKI(44) = ode.nproj; QR_PKI(45) = ode.checked;
-                QR_PKI(46) = k;
-                QR_PKI(47) = (int)busy | ((int)fin << 1) | ((int)need_init << 2) | ((int)has_next << 3) | ((int)exhausted << 4);
+                if (MULTI) QR_PKI(46) = k;
+                QR_PKI(47) = (int)busy | ((int)fin << 1) | ((int)need_init << 2) | ((int)has_next << 3) | ((int)exhausted << 4) | ((int)(MULTI && fresh) << 5);
                 QR_PKI(48) = (int32_t)(uint32_t)e; QR_PKI(49) = (int32_t)(e >> 32);
                 QR_PKI(50) = (int32_t)(uint32_t)e_next; QR_PKI(51) = (int32_t)(e_next >> 32);
                 QR_PKI(52) = (int32_t)(uint32_t)tile_base; QR_PKI(53) = (int32_t)(tile_base >> 32);
                 QR_PKI(54) = tile_pos; QR_PKI(55) = rq_n;
+                if (MULTI) { QR_PKI(56) = cq_n; QR_PKI(57) = k_next; }
                 if (do_reset) {
                     float dummy[23];
                     // the new episode's first observation replaces the terminal one in the step's output row
@@ -599,37 +633,37 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 d.fm = pk[32 * 32]; d.g = pk[33 * 32]; d.Mi0 = pk[34 * 32]; d.Mi1 = pk[35 * 32]; d.kw0 = pk[36 * 32]; d.kw1 = pk[37 * 32]; d.w3dot = pk[38 * 32];
                 ode.t = pk[39 * 32]; ode.h_abs = pk[40 * 32];
                 ode.rejected = QR_PKI(41); ode.nfev = QR_PKI(42); ode.status = QR_PKI(43); ode.nproj = QR_PKI(44); ode.checked = QR_PKI(45);
-                k = QR_PKI(46);
+                if (MULTI) k = QR_PKI(46);
                 {
                     const int fl = QR_PKI(47);
-                    busy = fl & 1; fin = (fl >> 1) & 1; need_init = (fl >> 2) & 1; has_next = (fl >> 3) & 1; exhausted = (fl >> 4) & 1;
+                    busy = fl & 1; fin = (fl >> 1) & 1; need_init = (fl >> 2) & 1; has_next = (fl >> 3) & 1; exhausted = (fl >> 4) & 1; fresh = (fl >> 5) & 1;
                 }
                 e = (int64_t)(((uint64_t)(uint32_t)QR_PKI(49) << 32) | (uint32_t)QR_PKI(48));
                 e_next = (int64_t)(((uint64_t)(uint32_t)QR_PKI(51) << 32) | (uint32_t)QR_PKI(50));
                 tile_base = (int64_t)(((uint64_t)(uint32_t)QR_PKI(53) << 32) | (uint32_t)QR_PKI(52));
                 tile_pos = QR_PKI(54); rq_n = QR_PKI(55);
+                if (MULTI) { cq_n = QR_PKI(56); k_next = QR_PKI(57); }
 #undef QR_PKI
                 if (do_reset) {
                     const T* sc = ks + lane * 32;   // what auto_reset_env left in this lane's scratch
-                    if (r_cont) {
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) x[i] = sc[i];
+                    for (int i = 0; i < 18; ++i) a.state[i * N + r_e] = sc[i];   // scratch order = state row order
 #pragma unroll
-                        for (int i = 0; i < 14; ++i) y[i] = sc[3 + i];
-                        W3 = sc[17];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) sh[(S_I + i) * 32] = sc[18 + i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 18; ++i) a.state[i * N + r_e] = sc[i];   // scratch order = state row order
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) a.integ[i * N + r_e] = sc[18 + i];
+                    for (int i = 0; i < 8; ++i) a.integ[i * N + r_e] = sc[18 + i];
+                }
+                if (MULTI) {   // envs with sub-steps left wait in CQ for a free lane (A0 of the coming rounds)
+                    const bool cont = do_reset && (r_k + 1 < NS);
+                    const unsigned cm = __ballot_sync(FULL, cont);
+                    if (cont) {
+                        const int q = cq_n + __popc(cm & ((1u << lane) - 1u));
+                        cq[q] = (int32_t)r_e; cqk[q] = (int16_t)(r_k + 1);
                     }
+                    cq_n += __popc(cm);
                 }
                 __syncwarp();
             }
         }
-        if (drained && (MULTI || rq_n == 0)) break;
+        if (drained && rq_n == 0 && cq_n == 0) break;
         // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
         if (busy && need_init) {
             need_init = false;
@@ -641,8 +675,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             T p_m, p_J1, p_J3, p_ctw, p_d = 0, p_ctf = 0;
             bool act_f32 = a.act_f32 != 0;
             const bool staged_act = a.actions && (a.act_f32 || sizeof(T) == 8);   // what A0 can stage (kernel-uniform)
-            if (k == 0) {
-                // first step of an env adopted in A2: action, parameters and b1d were fetched ahead into the stash
+            const bool staged = MULTI ? fresh : true;   // adopted in this round's A2: action, parameters and b1d were fetched ahead into the stash
+            fresh = false;
+            if (staged) {
                 cp_async_wait_group<1>();   // everything but A2's group (end-of-step values, not needed yet)
                 p_m = sh[(S_PAR + 0) * 32]; p_J1 = sh[(S_PAR + 2) * 32]; p_J3 = sh[(S_PAR + 3) * 32]; p_ctw = sh[(S_PAR + 5) * 32];
                 if (MODE == 0) { p_d = sh[(S_PAR + 1) * 32]; p_ctf = sh[(S_PAR + 4) * 32]; }
@@ -663,7 +698,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
                 }
             }
-            if (a.actions && !(k == 0 && staged_act)) {
+            if (a.actions && !(staged && staged_act)) {
                 const int64_t base = ((int64_t)k * N + e) * A;
                 if (a.act_f32) {
                     const float* p = (const float*)a.actions + base;
@@ -723,7 +758,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 traj_wd<T>(y + 3, Wv, b1d, Wd);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { sh[(S_B1D + i) * 32] = b1d[i]; sh[(S_WD + i) * 32] = Wd[i]; }   // for the observation at the end
-                if (k == a.n_steps - 1) {   // visible in the goal buffer like env.Wd after set_goal_state
+                if (k == NS - 1) {   // visible in the goal buffer like env.Wd after set_goal_state
 #pragma unroll
                     for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
                 }

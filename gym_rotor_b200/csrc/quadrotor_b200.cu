@@ -339,7 +339,7 @@ int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, fl
                uint8_t* done_out, void* stream)
 {
     int rc = check(h); if (rc) return rc;
-    if (n_steps <= 0) return fail(QR_ERR_INVALID, "qr_rollout: n_steps must be positive");
+    if (n_steps <= 0 || n_steps > 32767) return fail(QR_ERR_INVALID, "qr_rollout: n_steps must be in 1 .. 32767");
     if (n_steps > 1 && h->cfg.goal_mode >= QR_GOAL_TRAJ_HOVER)
         return fail(QR_ERR_INVALID, "qr_rollout: trajectory modes hover/circle/eight need qr_goal_update before every step (n_steps must be 1)");
     if (act_dtype == QR_ACT_POLICY) {

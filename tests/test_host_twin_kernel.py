@@ -215,8 +215,10 @@ def _reset_all(F, cfg, env, episode=1):
 
 @pytest.mark.parametrize("dtype64,act64", [(True, True), (False, False), (False, True), (True, False)])
 def test_kernel_rollout_with_autoreset_equals_single_steps(libs, dtype64, act64):
-    """Multi-step launch (reset at the parked call site, env stays in its lane) == single-step launches (queued resets,
-    batches of >= 24 and bursts of a common time limit), ragged n, misaligned rollout rows."""
+    """Multi-step launch (an env whose episode ends leaves its lane, is reset in a batch and waits in CQ for a free lane to
+    go on stepping) == single-step launches (queued resets, batches of >= 24 and bursts of a common time limit), ragged n,
+    misaligned rollout rows.  The float32 cases start from staggered episode lengths, so that lanes run out of phase and
+    envs are adopted from CQ and from the tile sequence in the same round."""
     K, F = libs
     n, steps = 203, 20
     kw = dict(n_envs=n, seed=5, autoreset=1, goal_mode=1, max_episode_steps=7)
@@ -224,6 +226,8 @@ def test_kernel_rollout_with_autoreset_equals_single_steps(libs, dtype64, act64)
     e1, e2 = HostEnv(K, c1, warps=2), HostEnv(K, c2, warps=5)
     _reset_all(F, c1, e1); _reset_all(F, c2, e2)
     rng = np.random.default_rng(15)
+    if not dtype64:
+        e1.ep_length[:] = rng.integers(0, 7, n); e2.ep_length[:] = e1.ep_length
     acts = rng.uniform(-1, 1, (steps, n, 4)).astype(np.float64 if act64 else np.float32)   # staged or loaded at the step start
     obs_r, rew_r, done_r = e1.launch(acts, n_steps=steps, store=True)
     for k in range(steps):

@@ -8,9 +8,12 @@ top_file = sys.argv[4] if len(sys.argv) > 4 else "qr_kernels.cuh"
 src_dir = os.path.join(os.path.dirname(os.path.abspath(lib)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l and l.rstrip().endswith(":")][0]
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):   # one cubin per translation unit
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+    hits = [i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l and l.rstrip().endswith(":")]
+    if hits:
+        break
+start = hits[0]
 
 # function start lines per source file (crude: lines that look like a device function header)
 funcs = {}

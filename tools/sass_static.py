@@ -9,9 +9,15 @@ top_file = sys.argv[3] if len(sys.argv) > 3 else "qr_kernels.cuh"
 if not obj.endswith(".cubin"):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
-    obj = os.path.join(tmp, [f for f in os.listdir(tmp) if f.endswith(".cubin")][0])
-dis = subprocess.run(["nvdisasm", "-gi", "-c", obj], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l and l.rstrip().endswith(":")][0]
+    cands = [os.path.join(tmp, f) for f in sorted(os.listdir(tmp)) if f.endswith(".cubin")]
+else:
+    cands = [obj]
+for obj in cands:   # the library holds one cubin per translation unit: take the one that has the kernel
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", obj], capture_output=True, text=True).stdout.split("\n")
+    hits = [i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l and l.rstrip().endswith(":")]
+    if hits:
+        break
+start = hits[0]
 src_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gym_rotor_b200", "csrc")
 funcs = {}
 for f in os.listdir(src_dir):
