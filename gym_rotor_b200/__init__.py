@@ -9,7 +9,7 @@ from ._native import NativeError, load  # noqa: F401
 
 def __getattr__(name):
     # torch-dependent classes are imported lazily so that `import gym_rotor_b200` stays cheap
-    if name in ("BatchedQuadEnv", "CoupledWrapper", "DecoupledWrapper", "QuadEnv", "QuadVectorEnv"):
+    if name in ("BatchedQuadEnv", "CoupledWrapper", "DecoupledWrapper", "QuadEnv", "QuadVectorEnv", "register_envs", "make_spaces"):
         from . import vec_env
         return getattr(vec_env, name)
     raise AttributeError(name)

@@ -18,10 +18,11 @@ GOAL_EXTERNAL, GOAL_TRAJ_MODE0, GOAL_TRAJ_HOVER, GOAL_TRAJ_CIRCLE, GOAL_TRAJ_EIG
 GOAL_TRAJ_TAKEOFF, GOAL_TRAJ_LAND, GOAL_TRAJ_STAY = 5, 6, 7
 ACT_POLICY = 2   # qr_rollout: actions from the shipped TD3 actor, evaluated inside the kernel
 ST_NONFINITE, ST_TOO_SMALL_STEP, ST_SVD = 1, 2, 4
-NUM_STATS = 16
+NUM_STATS = 20
+ABI_VERSION = 2
 STAT_NAMES = ["episodes", "return0", "return1", "length", "crashed", "truncated", "return0_sq", "steps",
               "bad_status", "nfev", "attempts_1", "attempts_2", "attempts_3", "attempts_4p", "reward0",
-              "so3_projections"]
+              "so3_projections", "bench_reward", "solved_at_limit", "reserved18", "reserved19"]
 
 # every symbol include/quadrotor_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = ["qr_default_config", "qr_create", "qr_destroy", "qr_get_config", "qr_get_buffers", "qr_reset",
@@ -33,7 +34,7 @@ class QrConfig(C.Structure):
     _fields_ = [("n_envs", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
                 ("mode", C.c_int32), ("dtype", C.c_int32), ("integrator", C.c_int32), ("autoreset", C.c_int32),
                 ("goal_mode", C.c_int32), ("env_type", C.c_int32), ("max_episode_steps", C.c_int32),
-                ("diagnostics", C.c_int32)] + [
+                ("diagnostics", C.c_int32), ("round_returns", C.c_int32), ("reserved1", C.c_int32)] + [
         (n, C.c_double) for n in (
             "dt", "g", "rtol", "atol", "x_lim", "v_lim", "W_lim", "eIx_lim", "eIb1_lim", "sat_sigma", "alpha", "beta",
             "Cx", "CIx", "Cv", "Cb1", "CIb1", "CW", "Cw12", "CW3", "reward_min", "reward_min_1", "reward_min_2",
@@ -78,7 +79,7 @@ def load():
     L.qr_policy_td3.argtypes = [vp, vp, vp]
     L.qr_step.argtypes = [vp, vp, C.c_int, vp]
     L.qr_rollout.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
-    L.qr_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.qr_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     L.qr_set_state_host.argtypes = [vp, vp, vp, vp, vp]
     L.qr_get_state_host.argtypes = [vp, vp, vp, vp, vp]
     L.qr_stats.argtypes = [vp, C.POINTER(C.c_double), C.c_int, vp]
@@ -89,6 +90,9 @@ def load():
     L.qr_obs_stride.restype = C.c_int
     for name in EXPORTS:
         getattr(L, name)
+    if L.qr_abi_version() != ABI_VERSION:
+        raise NativeError("%s has ABI version %d, this package needs %d: rebuild it (python -m gym_rotor_b200.build --force)"
+                          % (LIB_PATH, L.qr_abi_version(), ABI_VERSION))
     _lib = L
     return L
 

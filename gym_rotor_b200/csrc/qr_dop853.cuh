@@ -299,7 +299,7 @@ template <typename T> QR_DEV void rhs_z(const T* z, T W3, const Dyn<T>& d, T* k)
 
 // The acceptance test of ensure_SO3 (see so3_ok in qr_math.cuh) on the R part of a z vector.  Same tolerances; the
 // column products are packed, every comparison is ordered (a NaN fails), one predicate at the end.
-template <typename T> QR_DEV bool so3_ok_z(const T* z)
+template <typename T> QR_DEV bool so3_ok_z(const T* z, T* mx = nullptr)
 {
     using N = num<T>;
     const T tol = (T)1e-5;
@@ -321,6 +321,14 @@ template <typename T> QR_DEV bool so3_ok_z(const T* z)
     const T cy = N::fma(z[7], z[4], -(z[2] * z[8]));
     const T cz = N::fma(z[2], z[5], -(z[3] * z[4]));
     const T dm1 = N::fma(z[0], cx, N::fma(z[1], cy, N::fma(z[6], cz, (T)-1)));
+    if (mx) {
+        // speculative stages (stage_finish): the seven defects only feed three running maxima (diagonal, off-diagonal,
+        // determinant; NaN-propagating), compared once at the end of the attempt instead of seven times per stage
+        mx[0] = N::absmax2_nan(N::absmax3_nan(mx[0], e00, e11), e22);
+        mx[1] = N::absmax2_nan(N::absmax3_nan(mx[1], e01, e02), e12);
+        mx[2] = N::absmax2_nan(mx[2], dm1);
+        return true;
+    }
     return (N::abs(e00) <= tol + tol) & (N::abs(e11) <= tol + tol) & (N::abs(e22) <= tol + tol) & (N::abs(e01) <= tol) &
            (N::abs(e02) <= tol) & (N::abs(e12) <= tol) & (N::abs(dm1) <= (T)1e-8 + tol);
 }
@@ -372,7 +380,7 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
     }
     const T inv_sqrt_n = (T)0.23570226039551584;  // 1/sqrt(18)
     T d0 = N::sqrt(s0a + s0b) * inv_sqrt_n, d1 = N::sqrt(s1a + s1b) * inv_sqrt_n;
-    T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+    T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : N::div_fast((T)0.01 * d0, d1);
     h0 = (Tend < h0) ? Tend : h0;   // python min(h0, interval): keeps a NaN h0
     // Euler probe y1 = y0 + h0 f0 ; f1 = F(y1)
     T z1[14], k1[14];
@@ -402,10 +410,10 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
 #pragma unroll
         for (int i = 0; i < 3; ++i) { T a = dv[i] * iscx[i]; s2a = N::fma(a, a, s2a); }
     }
-    T d2 = N::sqrt(s2a + s2b) * inv_sqrt_n / h0;
+    T d2 = N::div_fast(N::sqrt(s2a + s2b) * inv_sqrt_n, h0);
     T h1;
     if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = N::max((T)1e-6, h0 * (T)1e-3);
-    else h1 = N::root8((T)0.01 / N::max(d1, d2));
+    else h1 = N::root8(N::div_fast((T)0.01, N::max(d1, d2)));
     T h_abs = (T)100 * h0;
     h_abs = (h1 < h_abs) ? h1 : h_abs;
     h_abs = (Tend < h_abs) ? Tend : h_abs;
@@ -420,7 +428,12 @@ template <typename T> struct AttCtx {
     T h;              // signed step
     T W3;             // W3 at the start of the step
     T xb[3], x5[3], x3[3];   // B / E5 / (E3 - B) weighted sums of the stage velocities (x' = v): order v0 v1 v2
-    bool all_ok;      // every stage matrix passed the SO(3) test
+    T so3mx[3];       // running maxima over the stages of the SO(3) defects |diag(RtR) - 1|, |offdiag(RtR)|, |det R - 1|
+    QR_DEV bool all_ok() const   // every stage matrix passed the SO(3) test (a NaN fails it)
+    {
+        const T tol = (T)1e-5;
+        return (so3mx[0] <= tol + tol) & (so3mx[1] <= tol) & (so3mx[2] <= (T)1e-8 + tol);
+    }
 };
 
 // Stage S: stage point zs = z + h P (P = sum_j a_Sj K_j, complete), SO(3) test, F = K_S = f(zs).  P is consumed.
@@ -442,7 +455,7 @@ QR_DEV void stage_finish(const T* z, T* P, const Dyn<T>& d, AttCtx<T>& c, T* F)
     // happens.  The stages therefore run SPECULATIVELY: the test is evaluated as plain dataflow (nothing waits
     // for it), and if some stage failed it the attempt is thrown away and redone by dop853_attempt_checked, which
     // re-projects stage by stage exactly like the reference does.
-    { const bool ok = so3_ok_z<T>(P); c.all_ok = c.all_ok & ok; }
+    so3_ok_z<T>(P, c.so3mx);
     rhs_z<T>(P, W3s, d, F);
 }
 
@@ -568,7 +581,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     T t_new = o.t + o.h_abs;
     if (t_new - Tend > (T)0) t_new = Tend;
     AttCtx<T> c;
-    c.h = t_new - o.t; c.W3 = W3; c.all_ok = true;
+    c.h = t_new - o.t; c.W3 = W3; c.so3mx[0] = c.so3mx[1] = c.so3mx[2] = 0;
     T z[14];
     to_z<T>(y, z);
     {   // stage 0 of the position sums: K0_x = v
@@ -616,7 +629,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
     for (int i = 0; i < 7; ++i) padd<T>(s3[2 * i], s3[2 * i + 1], sb[2 * i], sb[2 * i + 1], s3[2 * i], s3[2 * i + 1]);   // E3 sum = B sum + correction
     v_fma_out<T>(c.h, sb, z, sb);   // y_new
     if (!live) return false;
-    if (!c.all_ok) { o.checked = 1; return false; }   // redo this attempt with per-stage re-projection
+    if (!c.all_ok()) { o.checked = 1; return false; }   // redo this attempt with per-stage re-projection
     return dop853_conclude<T>(x, y, W3, d, Tend, rtol, atol, K0, o, c.h, t_new, too_small, z, sb, s5, s3, xnew, c.x5, x3, 0, 0);
 }
 

@@ -39,7 +39,7 @@ template <typename T> struct EnvConst {
     float nCx, nCIx, nCv, nCb1, nCIb1, nCW, nCw12, nCW3;   // negated reward coefficients, as float32 (numpy weak scalars)
     double Cx, Cv, Cb1, CW;                                // base Quad-v0 reward is evaluated in float64
     double rmin, rmin1, rmin2, slope, slope1, slope2, udm;
-    int mode, integrator, autoreset, goal_mode, env_type, max_episode_steps, diagnostics;
+    int mode, integrator, autoreset, goal_mode, env_type, max_episode_steps, diagnostics, round_returns;
 };
 
 // ---- Philox4x32-10 (Salmon et al., SC'11) ---------------------------------------------------------------

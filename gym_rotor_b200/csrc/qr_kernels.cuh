@@ -26,8 +26,12 @@ __host__ __device__ constexpr int obs_stride_of(int O) { return (O + 3) & ~3; }
 // (stall_no_instruction was the largest stall, 1.5 cycles per issued instruction); warps that pass the same code together
 // share the fetches.  Negative: groups by SM sub-partition (warp & 3).
 #ifndef QR_LOCKSTEP
-#define QR_LOCKSTEP 0
+#define QR_LOCKSTEP 0          // single-step launches
 #endif
+#ifndef QR_LOCKSTEP_MULTI
+#define QR_LOCKSTEP_MULTI 0    // multi-step launches (long-running: the warps of a block drift fully out of phase)
+#endif
+#define QR_NSTATS 20   // QR_NUM_STATS of include/quadrotor_b200.h
 #ifndef QR_KS_SLOTS_F32
 #define QR_KS_SLOTS_F32 6   // float32 keeps K2..K8 in slots 0..5 (qr_dop853.cuh); with 6 the block fits the 196 KB shared-memory configuration (60 KB of L1 instead of 28: +5 %, profiles/r02/r02e_ab.txt)
 #endif
@@ -228,7 +232,7 @@ template <typename T> struct warp_smem {
     static constexpr size_t slot_elems = (size_t)(sizeof(T) == 4 ? QR_KS_SLOTS_F32 : QR_NSLOTS) * QR_SLOT_ELEMS;
     static constexpr size_t ks_bytes = (slot_elems > park_elems ? slot_elems : park_elems) * sizeof(T);
     static constexpr size_t os_bytes = 32 * 36 * sizeof(T);   // the stash: 36 slots per lane
-    static constexpr size_t ws_bytes = 16 * sizeof(double);
+    static constexpr size_t ws_bytes = QR_NSTATS * sizeof(double);
     static constexpr int rq_cap = 64, cq_cap = 64;   // envs out of their lane never exceed QR_RESET_BATCH - 1 + 32 (see `parked reset`)
     static constexpr size_t rq_bytes = rq_cap * sizeof(int32_t);
     static constexpr size_t bytes = ks_bytes + os_bytes + ws_bytes + rq_bytes;   // multiple of 16
@@ -255,12 +259,13 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     const EnvConst<T>& c = a.c;
     const int64_t N = a.n;
     const int NS = MULTI ? a.n_steps : 1;   // single-step kernels: the sub-step counter k folds to the constant 0
+    constexpr int LOCKSTEP = MULTI ? QR_LOCKSTEP_MULTI : QR_LOCKSTEP;
     int grp_id = 0, grp_threads = 0;   // lock-step group of this warp: named barrier (1 + group), threads in it
-    if (QR_LOCKSTEP != 0) {
+    if (LOCKSTEP != 0) {
         const int nw = (int)(blockDim.x >> 5);
-        if (QR_LOCKSTEP > 0) {
-            grp_id = warp / QR_LOCKSTEP;
-            grp_threads = 32 * min(QR_LOCKSTEP, nw - grp_id * QR_LOCKSTEP);
+        if (LOCKSTEP > 0) {
+            grp_id = warp / LOCKSTEP;
+            grp_threads = 32 * min(LOCKSTEP, nw - grp_id * LOCKSTEP);
         } else {
             grp_id = warp & 3;
             grp_threads = 32 * ((nw - grp_id + 3) >> 2);
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     int16_t* const rqk = cqk + warp_smem<T>::cq_cap;
     const Philox ph{a.key0, a.key1};
 
-    if (lane < 16) ws[lane] = 0.0;
+    if (lane < QR_NSTATS) ws[lane] = 0.0;
     __syncwarp();
 
     // 32-env tiles are handed out dynamically (one atomic per tile on a per-launch counter): warps that drew
@@ -390,7 +395,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             __syncwarp();   // phase B is over for every lane: the stage storage may be reused as reset scratch
             bool ep_done = false, term = false, trunc = false;
             int nf = 0, st = 0, nproj = 0, ep_len_done = 0;
-            float rew0f = 0.f;
+            float rew0f = 0.f, brew = 0.f;
+            bool solved = false;
             T ret_done0 = 0, ret_done1 = 0;
             T In[8];                    // integral errors after this step
             T ep_ret0 = 0, ep_ret1 = 0; // episode accumulators after this step
@@ -475,11 +481,25 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     }
                 }
                 rew0f = (float)rew[0];
-                ep_ret0 += (T)rew[0];
-                if (G == 2) ep_ret1 += (T)rew[1];
+                if (c.round_returns) {   // the trainer's running return, main.py:180: float('{:.4f}'.format(ret + r)) every step
+                    ep_ret0 = (T)(rint(((double)ep_ret0 + rew[0]) * 1e4) / 1e4);   // k / 10^4 correctly rounded = float('0.dddd')
+                    if (G == 2) ep_ret1 = (T)(rint(((double)ep_ret1 + rew[1]) * 1e4) / 1e4);
+                } else {
+                    ep_ret0 += (T)rew[0];
+                    if (G == 2) ep_ret1 += (T)rew[1];
+                }
                 ep_len += 1;
                 term = (dn[0] | dn[1]) != 0;
                 trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
+                if (MODE != 0) {
+                    // benchmark_reward_func(ex, eb1) = interp(-|ex| - |eb1|, [-2, 0], [0, 1]) (utils/utils.py:21-47) on this
+                    // step's observation, and the trainer's "solved" relabel at the time limit (main.py:169-173)
+                    const float ex0 = o[0] * (float)c.x_lim, ex1 = o[1] * (float)c.x_lim, ex2 = o[2] * (float)c.x_lim;
+                    const float eb1 = o[MODE == 1 ? 18 : 15] * 3.14159265358979f;
+                    const float rb = -sqrtf(fmaf(ex2, ex2, fmaf(ex1, ex1, ex0 * ex0))) - fabsf(eb1);
+                    brew = fminf(fmaxf(fmaf(rb, 0.5f, 1.0f), 0.f), 1.f);
+                    solved = trunc && fabsf(ex0) <= 0.03f && fabsf(ex1) <= 0.03f && fabsf(ex2) <= 0.03f && rew[0] != -1.0;
+                }
                 // per-step scalar outputs
                 T* rw = a.reward_roll ? a.reward_roll + ((int64_t)k * N + e) * G : (last ? a.reward + e * G : nullptr);
                 uint8_t* dd = a.done_roll ? a.done_roll + ((int64_t)k * N + e) * G : (last ? a.done + e * G : nullptr);
@@ -540,8 +560,11 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 const unsigned m3 = __ballot_sync(FULL, fin && att == 3), m4 = __ballot_sync(FULL, fin && att >= 4);
                 const unsigned mbad = __ballot_sync(FULL, fin && st != 0);
                 const float s_rew = warp_sum_f(rew0f);
+                const float s_brew = (MODE != 0) ? warp_sum_f(brew) : 0.f;
+                const unsigned msolved = (MODE != 0) ? __ballot_sync(FULL, solved) : 0u;
                 const unsigned mres = __ballot_sync(FULL, ep_done);
                 if (lane == 0) {
+                    if (MODE != 0) { ws[16] += (double)s_brew; if (msolved) ws[17] += (double)__popc(msolved); }
                     ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev; ws[15] += (double)s_proj;
                     ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
                     ws[8] += (double)__popc(mbad); ws[14] += (double)s_rew;
@@ -694,7 +717,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 __syncwarp();
             }
         }
-        if (QR_LOCKSTEP == 0) {
+        if (LOCKSTEP == 0) {
             if (drained && rq_n == 0 && cq_n == 0) break;
         } else {
             // a warp without work keeps pace (idle rounds) until its whole group is done: the barrier counts every warp
@@ -752,7 +775,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                 }
             }
-            if (!GOAL1) {   // the observation at the end of this step reads the goal: have it in L2 by then
+            if (!GOAL1 && !(MODE != 0 && c.goal_mode >= 2)) {   // the observation at the end of this step reads the goal: have it in L2 by then
 #pragma unroll
                 for (int i = 0; i < 12; ++i) prefetch_l2(a.goal + i * N + e);
             }
@@ -789,6 +812,27 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             for (int i = 0; i < 14; ++i) r.y[i] = y[i];
             r.W3 = W3;
             r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
+            if (!GOAL1 && MODE != 0 && c.goal_mode >= 2) {
+                // trajectory_generator.get_desired(state, mode) + set_goal_state on the pre-step state, as the trainer calls
+                // them before every env.step (main.py:145-147): hover / circle / eight / take-off / land / stay.  Per-env
+                // trajectory state and goal go through their HBM arrays (the observation at the end of the step reads the
+                // goal from there, like an external one); kernel-uniform branch.
+                T ts[12], gl[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) { ts[i] = a.traj[i * N + e]; gl[i] = a.goal[i * N + e]; }
+                const T Wv[3] = {y[12], y[13], W3};
+                const int fl0 = (int)ts[1];
+                traj_desired<T>(traj_ref_mode<>(c.goal_mode), x, y, y + 3, Wv, ts, gl, (T)0, (T)0, c.dt);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) a.goal[i * N + e] = gl[i];
+                // per call only the clock, the flags and b1d_dot change; the rest is set when a trajectory (or the manual
+                // mode after it) starts
+                a.traj[0 * N + e] = ts[0]; a.traj[1 * N + e] = ts[1]; a.traj[9 * N + e] = ts[9]; a.traj[10 * N + e] = ts[10];
+                if (((int)ts[1] ^ fl0) & 5) {
+#pragma unroll
+                    for (int i = 2; i < 9; ++i) a.traj[i * N + e] = ts[i];
+                }
+            }
             if (GOAL1) {   // goal from the pre-step state, main.py:145-147
                 const T Wv[3] = {y[12], y[13], W3};
                 T Wd[3];
@@ -809,12 +853,15 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 d.kw0 = (p_J1 - p_J3) * rJ1; d.kw1 = (p_J3 - p_J1) * rJ1;
                 d.w3dot = M[2] * rJ3;
             }
-            bool finite = true;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) finite = finite && (num<T>::abs(x[i]) <= num<T>::huge);
-#pragma unroll
-            for (int i = 0; i < 14; ++i) finite = finite && (num<T>::abs(y[i]) <= num<T>::huge);
-            finite = finite && (num<T>::abs(W3) <= num<T>::huge);
+            // all 18 state words finite?  0 * v is (+-)0 for a finite v and NaN otherwise: one probe sum instead of 18 comparisons
+            // (pairs as the integrator's internal order holds them, qr_dop853.cuh)
+            T fp0 = 0, fp1 = 0;
+            pfma<T>((T)0, y[3], y[4], fp0, fp1, fp0, fp1); pfma<T>((T)0, y[6], y[7], fp0, fp1, fp0, fp1);
+            pfma<T>((T)0, y[9], y[10], fp0, fp1, fp0, fp1); pfma<T>((T)0, y[5], y[8], fp0, fp1, fp0, fp1);
+            pfma<T>((T)0, y[11], y[2], fp0, fp1, fp0, fp1); pfma<T>((T)0, y[0], y[1], fp0, fp1, fp0, fp1);
+            pfma<T>((T)0, y[12], y[13], fp0, fp1, fp0, fp1); pfma<T>((T)0, x[0], x[1], fp0, fp1, fp0, fp1);
+            pfma<T>((T)0, x[2], W3, fp0, fp1, fp0, fp1);
+            const bool finite = (fp0 + fp1) == (T)0;
             if (!finite) {
                 // scipy raises ValueError on a non-finite y0; flagged instead, state left as it is
                 ode.t = c.dt; ode.h_abs = 0; ode.rejected = 0; ode.nfev = 0; ode.status = 1; ode.nproj = 0;
@@ -867,7 +914,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 
     // ---- flush this warp's statistics: one atomic per non-zero statistic ----
     __syncwarp();
-    if (lane < 16 && ws[lane] != 0.0) atomicAdd(&a.stats[lane], ws[lane]);
+    if (lane < QR_NSTATS && ws[lane] != 0.0) atomicAdd(&a.stats[lane], ws[lane]);
 }
 
 // ---- env.reset(env_type) -----------------------------------------------------------------------------------
@@ -993,6 +1040,15 @@ __global__ void __launch_bounds__(QR_BLOCK) k_actor_td3(const float* __restrict_
 #pragma unroll
         for (int i = 0; i < A; ++i) act[(e0 + tid) * A + i] = a[i];
     }
+}
+
+// ---- observation rows without their padding ([rows][OS] -> [rows][O]); qr_step_host copies the dense block to the host ----
+static __global__ void k_dense_rows(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int O, int OS)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * O) return;
+    const int64_t r = i / O; const int c = (int)(i - r * O);
+    dst[i] = src[r * OS + c];
 }
 
 // ---- host-layout <-> device-layout (row-major [n][C] doubles <-> [C][n] T) -----------------------------------

@@ -59,6 +59,27 @@ template <> struct num<float> {
 #else
     static QR_DEV float recip(float x) { return 1.0f / x; }
 #endif
+    // max(acc, |a|, |b|) that PROPAGATES a NaN (fmaxf drops it): a running maximum whose final comparison fails on a NaN
+    // like every comparison of the quantities it absorbed would have
+#if QR_PTX
+    static QR_DEV float absmax3_nan(float acc, float a, float b)
+    {
+        float r;
+        asm("{\n\t.reg .f32 ta, tb;\n\tabs.f32 ta, %2;\n\tabs.f32 tb, %3;\n\tmax.NaN.f32 %0, %1, ta, tb;\n\t}" : "=f"(r) : "f"(acc), "f"(a), "f"(b));
+        return r;
+    }
+    static QR_DEV float absmax2_nan(float acc, float a)
+    {
+        float r;
+        asm("{\n\t.reg .f32 ta;\n\tabs.f32 ta, %2;\n\tmax.NaN.f32 %0, %1, ta;\n\t}" : "=f"(r) : "f"(acc), "f"(a));
+        return r;
+    }
+#else
+    static QR_DEV float absmax3_nan(float acc, float a, float b) { return (acc != acc || a != a || b != b) ? NAN : fmaxf(acc, fmaxf(fabsf(a), fabsf(b))); }
+    static QR_DEV float absmax2_nan(float acc, float a) { return (acc != acc || a != a) ? NAN : fmaxf(acc, fabsf(a)); }
+#endif
+    // quotient where a relative error of ~2 ulp is immaterial (step-size heuristics): MUFU.RCP + multiply, no slow path
+    static QR_DEV float div_fast(float a, float b) { return a * recip(b); }
     static constexpr float eps_jacobi = 1e-7f;
     static constexpr float huge = 3.0e38f;
 };
@@ -77,6 +98,9 @@ template <> struct num<double> {
     static QR_DEV double root8(double x) { return ::sqrt(::sqrt(::sqrt(x))); }
     static QR_DEV double inv_root8(double x) { return 1.0 / ::sqrt(::sqrt(::sqrt(x))); }
     static QR_DEV double recip(double x) { return 1.0 / x; }
+    static QR_DEV double absmax3_nan(double acc, double a, double b) { return (acc != acc || a != a || b != b) ? (acc + a + b) : fmax(acc, fmax(fabs(a), fabs(b))); }
+    static QR_DEV double absmax2_nan(double acc, double a) { return (acc != acc || a != a) ? (acc + a) : fmax(acc, fabs(a)); }
+    static QR_DEV double div_fast(double a, double b) { return a / b; }   // float64 is the parity mode: numpy's exact quotient
     static constexpr double eps_jacobi = 1e-16;
     static constexpr double huge = 1.0e300;
 };

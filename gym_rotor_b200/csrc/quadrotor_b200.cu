@@ -49,8 +49,10 @@ struct qr_handle {
     // staging for the *_host calls
     void* d_actions; size_t d_actions_bytes;
     double* d_stage; size_t d_stage_bytes;
-    cudaStream_t io_stream;
-    unsigned long long* tile_counter;
+    float* d_obs_dense; size_t d_obs_dense_bytes;   // qr_step_host: observation rows without the padding, chunk by chunk
+    cudaStream_t io_stream[2];      // qr_step_host pipelines its chunks over these two
+    cudaEvent_t io_event[3];        // [0]: the caller's stream at entry; [1], [2]: the io streams at exit
+    unsigned long long* tile_counter;   // [3]: launches on the caller's stream, on io_stream[0], on io_stream[1]
     int num_sms; int smem_optin; int attr_set[16];
 };
 
@@ -74,6 +76,7 @@ template <typename T> qr::StepArgs<T> make_args(const qr_handle* h)
     a.c.slope = 1.0 / (0.0 - c.reward_min); a.c.slope1 = 1.0 / (0.0 - c.reward_min_1); a.c.slope2 = 1.0 / (0.0 - c.reward_min_2);
     a.c.mode = c.mode; a.c.integrator = c.integrator; a.c.autoreset = c.autoreset; a.c.goal_mode = c.goal_mode;
     a.c.env_type = c.env_type; a.c.max_episode_steps = c.max_episode_steps; a.c.diagnostics = c.reserved0;
+    a.c.round_returns = c.round_returns;
     a.n = c.n_envs; a.env_lo = 0; a.env_hi = c.n_envs; a.env_id_offset = c.env_id_offset;
     a.key0 = (uint32_t)c.seed; a.key1 = (uint32_t)(c.seed >> 32);
     a.state = (T*)h->state; a.integ = (T*)h->integ; a.params = (T*)h->params; a.goal = (T*)h->goal; a.traj = (T*)h->traj;
@@ -96,8 +99,9 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     const bool policy = act_dtype == QR_ACT_POLICY;   // actions from the shipped actor, evaluated inside the kernel
     a.actions = policy ? nullptr : actions; a.act_f32 = (act_dtype == QR_F32); a.n_steps = n_steps;
     a.obs_roll = obs_roll; a.reward_roll = (T*)reward_roll; a.done_roll = done_roll;
-    // launches on different streams (qr_step_host pipelines two) must not share a tile counter
-    a.tile_counter = h->tile_counter + ((s == h->io_stream) ? 1 : 0);
+    // launches that may overlap must not share a tile counter: the two streams of qr_step_host have their own.  (Launches
+    // of one handle on several CALLER streams at once are not supported: they would race on the env state anyway.)
+    a.tile_counter = h->tile_counter + ((s == h->io_stream[0]) ? 1 : (s == h->io_stream[1]) ? 2 : 0);
     QR_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), s));
     // persistent warps: one CTA per SM, as many warps as the stage storage in shared memory allows
     const size_t per_warp = qr::warp_smem<T>::bytes;
@@ -151,6 +155,7 @@ int qr_default_config(qr_config* c, int mode, int dtype)
     c->mode = mode; c->dtype = dtype; c->integrator = QR_INT_DOP853;
     c->autoreset = 0; c->goal_mode = QR_GOAL_EXTERNAL; c->env_type = QR_ENV_TRAIN;
     c->max_episode_steps = 0; c->reserved0 = 1;               /* reserved0 = diagnostics (write nfev) */
+    c->round_returns = 0; c->reserved1 = 0;
     c->dt = 1. / 200; c->g = 9.81; c->rtol = 1e-3; c->atol = 1e-6;
     c->x_lim = 1.0; c->v_lim = 4.0; c->W_lim = 2 * 3.14159265358979323846;
     c->eIx_lim = 3.0; c->eIb1_lim = 3.0; c->sat_sigma = 1.; c->alpha = 0.01; c->beta = 0.05;
@@ -198,7 +203,7 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
         {(void**)&h->terminated, n}, {(void**)&h->truncated, n}, {(void**)&h->final_obs, n * obs_stride_of(h->O) * 4},
         {(void**)&h->nfev, n * 4}, {(void**)&h->status, n}, {&h->ep_return, 2 * n * E}, {(void**)&h->ep_length, n * 4},
         {(void**)&h->ep_index, n * 4}, {(void**)&h->stats, QR_NUM_STATS * sizeof(double)},
-        {(void**)&h->tile_counter, 2 * sizeof(unsigned long long)}};
+        {(void**)&h->tile_counter, 3 * sizeof(unsigned long long)}};
     for (auto& al : allocs) {
         cudaError_t ce = cudaMalloc(al.p, al.bytes);
         if (ce != cudaSuccess) {
@@ -208,7 +213,8 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
         }
         cudaMemset(*al.p, 0, al.bytes);
     }
-    QR_CUDA(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
+    for (auto& st : h->io_stream) QR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& ev : h->io_event) QR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     QR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     QR_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     h->smem_optin -= 256;    // reserve
@@ -234,9 +240,10 @@ int qr_destroy(qr_handle* h)
     if (!h) return QR_OK;
     cudaSetDevice(h->device);
     void* ptrs[] = {h->tile_counter, h->traj, h->state, h->integ, h->params, h->goal, h->obs, h->reward, h->done, h->terminated, h->truncated,
-                    h->final_obs, h->nfev, h->status, h->ep_return, h->ep_length, h->ep_index, h->stats, h->d_actions, h->d_stage};
+                    h->final_obs, h->nfev, h->status, h->ep_return, h->ep_length, h->ep_index, h->stats, h->d_actions, h->d_stage, h->d_obs_dense};
     for (void* p : ptrs) if (p) cudaFree(p);
-    if (h->io_stream) cudaStreamDestroy(h->io_stream);
+    for (auto st : h->io_stream) if (st) cudaStreamDestroy(st);
+    for (auto ev : h->io_event) if (ev) cudaEventDestroy(ev);
     delete h;
     return QR_OK;
 }
@@ -340,8 +347,6 @@ int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, fl
 {
     int rc = check(h); if (rc) return rc;
     if (n_steps <= 0 || n_steps > 32767) return fail(QR_ERR_INVALID, "qr_rollout: n_steps must be in 1 .. 32767");
-    if (n_steps > 1 && h->cfg.goal_mode >= QR_GOAL_TRAJ_HOVER)
-        return fail(QR_ERR_INVALID, "qr_rollout: trajectory modes hover/circle/eight need qr_goal_update before every step (n_steps must be 1)");
     if (act_dtype == QR_ACT_POLICY) {
         if (actions) return fail(QR_ERR_INVALID, "qr_rollout: act_dtype QR_ACT_POLICY takes no action array");
         if (h->cfg.mode == QR_MODE_QUAD) return fail(QR_ERR_INVALID, "qr_rollout: the shipped actors exist for the wrapper modes only");
@@ -351,7 +356,8 @@ int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, fl
     return launch_step<float>(h, 0, h->cfg.n_envs, actions, act_dtype, n_steps, obs_out, reward_out, done_out, s);
 }
 
-int qr_step_host(qr_handle* h, const void* actions_host, int act_dtype, float* obs_host, void* reward_host, uint8_t* done_host)
+int qr_step_host(qr_handle* h, const void* actions_host, int act_dtype, float* obs_host, void* reward_host, uint8_t* done_host,
+                 void* stream)
 {
     int rc = check(h); if (rc) return rc;
     if (!actions_host) return fail(QR_ERR_INVALID, "qr_step_host: null actions");
@@ -365,37 +371,52 @@ int qr_step_host(qr_handle* h, const void* actions_host, int act_dtype, float* o
         QR_CUDA(cudaMalloc(&h->d_actions, abytes));
         h->d_actions_bytes = abytes;
     }
-    cudaStream_t s = h->io_stream;
-    // Chunked pipeline on one stream: copy-in, step and copy-out of chunk i overlap chunk i+1 through the
-    // copy engines; chunk boundaries are multiples of the block size so obs tiles stay line aligned.
+    const int OS = obs_stride_of(h->O);
+    const bool dense_copy = obs_host && OS != h->O;   // padded device rows: compact them on the device, then ONE flat copy per chunk
+    if (dense_copy && h->d_obs_dense_bytes < (size_t)n * h->O * 4) {
+        if (h->d_obs_dense) cudaFree(h->d_obs_dense);
+        h->d_obs_dense = nullptr; h->d_obs_dense_bytes = 0;
+        QR_CUDA(cudaMalloc((void**)&h->d_obs_dense, (size_t)n * h->O * 4));
+        h->d_obs_dense_bytes = (size_t)n * h->O * 4;
+    }
+    // order the pipeline after whatever the caller has in flight on its stream (a reset, a goal, an earlier step)
+    QR_CUDA(cudaEventRecord(h->io_event[0], (cudaStream_t)stream));
+    for (auto st : h->io_stream) QR_CUDA(cudaStreamWaitEvent(st, h->io_event[0], 0));
+    // Chunked pipeline over the handle's two streams: copy-in, step and copy-out of chunk i overlap those of chunk i+1
+    // through the copy engines; chunk boundaries are multiples of the block size so rows stay line aligned.
     const int64_t target_chunks = 8;
     int64_t chunk = ((n + target_chunks - 1) / target_chunks + qr::QR_BLOCK - 1) / qr::QR_BLOCK * qr::QR_BLOCK;
     if (chunk < 16384) chunk = 16384;
-    cudaStream_t s2;  // second stream so that D2H of chunk i runs while chunk i+1 computes
-    static thread_local cudaStream_t aux = nullptr;
-    if (!aux) QR_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-    s2 = aux;
     int idx = 0;
     for (int64_t lo = 0; lo < n; lo += chunk, ++idx) {
         const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
-        cudaStream_t cs = (idx & 1) ? s2 : s;
+        cudaStream_t cs = h->io_stream[idx & 1];
         QR_CUDA(cudaMemcpyAsync((char*)h->d_actions + (size_t)lo * h->A * asz, (const char*)actions_host + (size_t)lo * h->A * asz,
                                 (size_t)(hi - lo) * h->A * asz, cudaMemcpyHostToDevice, cs));
         if (h->cfg.dtype == QR_F64) rc = launch_step<double>(h, lo, hi, h->d_actions, act_dtype, 1, nullptr, nullptr, nullptr, cs);
         else rc = launch_step<float>(h, lo, hi, h->d_actions, act_dtype, 1, nullptr, nullptr, nullptr, cs);
         if (rc) return rc;
         if (obs_host) {
-            const int OS = obs_stride_of(h->O);
-            if (OS == h->O) QR_CUDA(cudaMemcpyAsync(obs_host + (size_t)lo * h->O, h->obs + (size_t)lo * h->O, (size_t)(hi - lo) * h->O * 4, cudaMemcpyDeviceToHost, cs));
-            else QR_CUDA(cudaMemcpy2DAsync(obs_host + (size_t)lo * h->O, (size_t)h->O * 4, h->obs + (size_t)lo * OS, (size_t)OS * 4,
-                                           (size_t)h->O * 4, (size_t)(hi - lo), cudaMemcpyDeviceToHost, cs));   // padded rows (QR_OBS_PAD)
+            const float* src = h->obs + (size_t)lo * OS;
+            if (dense_copy) {
+                const int64_t tot = (hi - lo) * h->O;
+                qr::k_dense_rows<<<(unsigned)((tot + 255) / 256), 256, 0, cs>>>(src, h->d_obs_dense + (size_t)lo * h->O, hi - lo, h->O, OS);
+                g_launches++;
+                QR_CUDA(cudaGetLastError());
+                src = h->d_obs_dense + (size_t)lo * h->O;
+            }
+            QR_CUDA(cudaMemcpyAsync(obs_host + (size_t)lo * h->O, src, (size_t)(hi - lo) * h->O * 4, cudaMemcpyDeviceToHost, cs));
         }
         if (reward_host) QR_CUDA(cudaMemcpyAsync((char*)reward_host + (size_t)lo * h->G * h->elem, (char*)h->reward + (size_t)lo * h->G * h->elem,
                                                  (size_t)(hi - lo) * h->G * h->elem, cudaMemcpyDeviceToHost, cs));
         if (done_host) QR_CUDA(cudaMemcpyAsync(done_host + (size_t)lo * h->G, h->done + (size_t)lo * h->G, (size_t)(hi - lo) * h->G, cudaMemcpyDeviceToHost, cs));
     }
-    QR_CUDA(cudaStreamSynchronize(s));
-    QR_CUDA(cudaStreamSynchronize(s2));
+    // later work on the caller's stream is ordered after the pipeline; the call itself returns when the host buffers are valid
+    for (int i = 0; i < 2; ++i) {
+        QR_CUDA(cudaEventRecord(h->io_event[1 + i], h->io_stream[i]));
+        QR_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->io_event[1 + i], 0));
+    }
+    for (auto st : h->io_stream) QR_CUDA(cudaStreamSynchronize(st));
     return QR_OK;
 }
 
@@ -449,12 +470,12 @@ int qr_get_state_host(qr_handle* h, double* state, double* integ, double* params
     return QR_OK;
 }
 
-int qr_stats(qr_handle* h, double* out16, int reset_after, void* stream)
+int qr_stats(qr_handle* h, double* out, int reset_after, void* stream)
 {
     int rc = check(h); if (rc) return rc;
-    if (!out16) return fail(QR_ERR_INVALID, "qr_stats: null output");
+    if (!out) return fail(QR_ERR_INVALID, "qr_stats: null output");
     cudaStream_t s = (cudaStream_t)stream;
-    QR_CUDA(cudaMemcpyAsync(out16, h->stats, QR_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, s));
+    QR_CUDA(cudaMemcpyAsync(out, h->stats, QR_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (reset_after) QR_CUDA(cudaMemsetAsync(h->stats, 0, QR_NUM_STATS * sizeof(double), s));
     QR_CUDA(cudaStreamSynchronize(s));
     return QR_OK;

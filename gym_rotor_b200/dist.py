@@ -2,13 +2,13 @@
 
 Envs never interact: GPU g owns global envs [g*N/G, (g+1)*N/G) and the Philox streams are
 keyed by the GLOBAL env id, so results do not depend on G.  The only traffic is a sum all-reduce of the
-16-double episode-statistics vector once per rollout (128 bytes: latency bound, NCCL over NVLink).
+20-double episode-statistics vector once per rollout (160 bytes: latency bound, NCCL over NVLink).
 """
 import numpy as np
 import torch
 import torch.distributed as dist
 
-NUM_STATS = 16
+from ._native import NUM_STATS
 
 
 def shard_range(n_total, rank, world):
@@ -21,7 +21,7 @@ def shard_range(n_total, rank, world):
 
 
 def reduce_stats_tensor(stats, group=None):
-    """Sum-all-reduces a [16] float64 tensor in place (works on NCCL/CUDA and gloo/CPU tensors)."""
+    """Sum-all-reduces a [NUM_STATS] float64 tensor in place (works on NCCL/CUDA and gloo/CPU tensors)."""
     if stats.numel() != NUM_STATS or stats.dtype != torch.float64:
         raise ValueError("stats must be a float64 tensor with %d elements" % NUM_STATS)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -48,4 +48,6 @@ def summarize(stats):
             "mean_episode_length": s[3] / ep, "crashed": s[4], "truncated": s[5], "steps": s[7],
             "bad_status": s[8], "mean_rhs_evals": s[9] / max(s[7], 1.0),
             "attempt_hist": (s[10:14] / max(s[7], 1.0)).tolist(), "mean_reward_agent0": s[14] / max(s[7], 1.0),
-            "so3_projections_per_step": s[15] / max(s[7], 1.0)}
+            "so3_projections_per_step": s[15] / max(s[7], 1.0),
+            "mean_benchmark_reward": s[16] / max(s[7], 1.0),      # utils/utils.py:21-47, per env-step
+            "solved_at_time_limit": s[17]}                        # main.py:169-173

@@ -94,6 +94,16 @@ class BatchedQuadEnv:
             if not hasattr(cfg, k):
                 raise TypeError("unknown config field %r" % k)
             setattr(cfg, k, v)
+        # values the reference derives from the coefficients (quad.py:80-88, decoupled_yaw_wrapper.py:29-33) follow the
+        # overrides unless they were overridden themselves
+        if "CW" not in overrides:
+            cfg.CW = cfg.Cw12
+        if "reward_min" not in overrides:
+            cfg.reward_min = -np.ceil(cfg.Cx + cfg.CIx + cfg.Cv + cfg.Cb1 + cfg.CIb1 + cfg.CW)
+        if "reward_min_1" not in overrides:
+            cfg.reward_min_1 = -np.ceil(cfg.Cx + cfg.CIx + cfg.Cv + cfg.Cw12)
+        if "reward_min_2" not in overrides:
+            cfg.reward_min_2 = -np.ceil(cfg.Cb1 + cfg.CW3 + cfg.CIb1)
         self.cfg = cfg
         self._h = C.c_void_p()
         nat.check(self._L.qr_create(C.byref(cfg), self._dev_index, C.byref(self._h)))
@@ -166,11 +176,12 @@ class BatchedQuadEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    @staticmethod
-    def _mask_ptr(mask):
+    def _mask_ptr(self, mask):
         if mask is None:
             return None, None
-        m = mask.to(torch.uint8).contiguous()
+        m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()   # the kernels read it on the device
+        if tuple(m.shape) != (self.num_envs,):
+            raise ValueError("mask must have shape (%d,)" % self.num_envs)
         return m, C.c_void_p(m.data_ptr())
 
     # ---- reference methods, batched ----
@@ -186,7 +197,8 @@ class BatchedQuadEnv:
         nat.check(self._L.qr_init_goal(self._h, p, self._stream()))
 
     def goal_update(self):
-        """trajectory_generator.get_desired + set_goal_state for the hover / circle / eight goal modes (no-op otherwise)."""
+        """ONE trajectory_generator.get_desired + set_goal_state call without stepping (hover ... stay goal modes; no-op
+        otherwise).  step() / rollout() / step_host() make this call themselves before every env.step."""
         nat.check(self._L.qr_goal_update(self._h, self._stream()))
 
     def get_current_state(self):
@@ -220,8 +232,8 @@ class BatchedQuadEnv:
             action = action.to(self.device).contiguous()
         if tuple(action.shape) != (self.num_envs, self.act_dim):
             raise ValueError("action must have shape (%d, %d)" % (self.num_envs, self.act_dim))
-        if self.cfg.goal_mode >= nat.GOAL_TRAJ_HOVER:
-            self.goal_update()      # trajectory_generator.get_desired on the pre-step state, main.py:145-147
+        # (goal modes hover ... stay: the step kernel evaluates trajectory_generator.get_desired on the pre-step state
+        #  itself, where the trainer calls it, main.py:145-147)
         nat.check(self._L.qr_step(self._h, C.c_void_p(action.data_ptr()),
                                   nat.F64 if action.dtype == torch.float64 else nat.F32, self._stream()))
         return self._split_obs(self.obs), self.reward, self.done.view(torch.bool), False, {}   # flags are 0/1 bytes: reinterpreted, not copied
@@ -261,15 +273,33 @@ class BatchedQuadEnv:
         return obs, rew, dn
 
     def step_host(self, actions, obs_out=None, reward_out=None, done_out=None):
-        """End-to-end step with HOST buffers (numpy arrays or pinned CPU tensors): H2D + step + D2H."""
-        def ptr(x):
+        """End-to-end step with HOST buffers (numpy arrays or pinned CPU tensors): H2D + step + D2H, ordered after the work
+        enqueued on the current torch stream.  Buffers must be C-contiguous host memory of exactly the shapes / dtypes
+        actions [N,A] float32|float64, obs [N,O] float32, reward [N,G] float32|float64 (the env's dtype), done [N,G] uint8|bool."""
+        N = self.num_envs
+        rdt = np.float64 if self.dtype == torch.float64 else np.float32
+
+        def ptr(x, name, shape, dtypes):
             if x is None:
                 return None
-            return C.c_void_p(x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data)
-        dt = actions.dtype
-        is64 = dt in (torch.float64, np.float64, np.dtype("float64"))
-        nat.check(self._L.qr_step_host(self._h, ptr(actions), nat.F64 if is64 else nat.F32, ptr(obs_out),
-                                       ptr(reward_out), ptr(done_out)))
+            if isinstance(x, torch.Tensor):
+                if x.device.type != "cpu":
+                    raise ValueError("step_host: %s must be host memory (use step() for device tensors)" % name)
+                ok, dt, p = x.is_contiguous(), np.dtype(str(x.dtype).replace("torch.", "")), x.data_ptr()
+            else:
+                x = np.asarray(x) if not isinstance(x, np.ndarray) else x
+                ok, dt, p = x.flags["C_CONTIGUOUS"], x.dtype, x.ctypes.data
+            if tuple(x.shape) != shape or not ok or dt not in [np.dtype(d) for d in dtypes]:
+                raise ValueError("step_host: %s must be C-contiguous, shape %s, dtype in %s" % (name, shape, [np.dtype(d).name for d in dtypes]))
+            return C.c_void_p(p)
+        pa = ptr(actions, "actions", (N, self.act_dim), (np.float32, np.float64))
+        if pa is None:
+            raise ValueError("step_host: actions are required")
+        is64 = str(actions.dtype).endswith("float64")
+        nat.check(self._L.qr_step_host(self._h, pa, nat.F64 if is64 else nat.F32,
+                                       ptr(obs_out, "obs_out", (N, self.obs_dim), (np.float32,)),
+                                       ptr(reward_out, "reward_out", (N, self.n_agents), (rdt,)),
+                                       ptr(done_out, "done_out", (N, self.n_agents), (np.uint8, np.bool_)), self._stream()))
 
     # ---- state injection / extraction (row-major [N,..] float64 host arrays) ----
     def set_state(self, state=None, integ=None, params=None, goal=None):
@@ -403,21 +433,96 @@ class FlightLog:
                 f.write(" ".join("%.10f" % v for v in r) + "\n")
 
 
-class QuadVectorEnv:
-    """gymnasium.vector.VectorEnv-shaped facade (gymnasium itself is not installed in this image).
+def _gymnasium():
+    """gymnasium if it is importable (it is not installed in the build image; the reference depends on it), else None."""
+    try:
+        import gymnasium
+        import gymnasium.vector  # noqa: F401
+        return gymnasium
+    except Exception:
+        return None
 
-    reset() -> (obs, info); step(actions) -> (obs, reward, terminated, truncated, info) with same-step
-    auto reset done in-kernel: the returned obs of a finished env is the first observation of its next
-    episode (main.py:226-230) and info['final_obs'] holds the terminal one.
+
+class TupleSpace:
+    """Stand-in for gymnasium.spaces.Tuple (used only when gymnasium is absent)."""
+
+    def __init__(self, spaces):
+        self.spaces = tuple(spaces)
+
+    def __len__(self):
+        return len(self.spaces)
+
+    def __getitem__(self, i):
+        return self.spaces[i]
+
+    def seed(self, seed=None):
+        return [sp.seed(seed) for sp in self.spaces]
+
+    def sample(self):
+        return tuple(sp.sample() for sp in self.spaces)
+
+
+def make_spaces(framework, num_envs, cfg):
+    """(single_observation_space, single_action_space, observation_space, action_space) of a vector env.
+
+    Quad-v0: exactly the boxes the reference declares (quad.py:104-132: raw-state bounds, actions in [-1, 1]^4).  The wrappers
+    inherit that declaration in the reference although they return NORMALISED observations (23 values, or 15 + 3 for the
+    two agents); a vector env has to describe what step() returns, so for them the observation space is the normalised box
+    [-1, 1]^O (errors are divided by their limits, quad.py:421-466; R and b3 entries are direction cosines), a Tuple of the
+    two agents' boxes for DecoupledWrapper.  gymnasium's classes are used when gymnasium is importable."""
+    gym = _gymnasium()
+    BoxT = gym.spaces.Box if gym else Box
+    TupT = gym.spaces.Tuple if gym else TupleSpace
+    A = 5 if framework == "MODUL" else 4
+
+    def build(n):
+        lead = () if n is None else (n,)
+        if framework == "QUAD":
+            hi = np.concatenate([cfg.x_lim * np.ones(3), cfg.v_lim * np.ones(3), np.ones(9), cfg.W_lim * np.ones(3)]).astype(np.float32)
+            hi = np.broadcast_to(hi, lead + (18,)).copy()
+            obs = BoxT(low=-hi, high=hi, dtype=np.float32)
+        elif framework == "MONO":
+            obs = BoxT(low=-1.0, high=1.0, shape=lead + (23,), dtype=np.float32)
+        else:
+            obs = TupT((BoxT(low=-1.0, high=1.0, shape=lead + (15,), dtype=np.float32),
+                        BoxT(low=-1.0, high=1.0, shape=lead + (3,), dtype=np.float32)))
+        act = BoxT(low=-1.0, high=1.0, shape=lead + (A,), dtype=np.float32)
+        return obs, act
+    so, sa = build(None)
+    bo, ba = build(num_envs)
+    return so, sa, bo, ba
+
+
+_VecBase = (_gymnasium().vector.VectorEnv if _gymnasium() else object)
+
+
+class QuadVectorEnv(_VecBase):
+    """gymnasium.vector.VectorEnv over the device-resident batch (a subclass of it whenever gymnasium is importable; the
+    build image does not have it, so there it is a plain class with the same attributes and methods).
+
+    reset() -> (obs, info); step(actions) -> (obs, reward, terminated, truncated, info) with same-step auto reset done
+    in-kernel (gymnasium's AutoresetMode.SAME_STEP): the returned obs of a finished env is the first observation of its
+    next episode (main.py:226-230) and info['final_obs'] holds the terminal one.  Tensors stay on the device.
+    Attributes: num_envs, single_observation_space, single_action_space, observation_space, action_space (make_spaces),
+    spec-like `max_episode_steps`.
     """
 
+    metadata = {"render_modes": [], "autoreset_mode": "SameStep"}
+
     def __init__(self, num_envs, framework="MONO", max_episode_steps=4000, goal_mode="traj0", **kw):
-        self.env = BatchedQuadEnv(num_envs, framework=framework, autoreset=True, goal_mode=goal_mode,
+        self.env = BatchedQuadEnv(num_envs, framework=framework, autoreset=True,
+                                  goal_mode=(goal_mode if framework != "QUAD" else "external"),
                                   max_episode_steps=max_episode_steps, **kw)
         self.num_envs = num_envs
+        self.framework = framework
+        self.max_episode_steps = max_episode_steps
+        (self.single_observation_space, self.single_action_space,
+         self.observation_space, self.action_space) = make_spaces(framework, num_envs, self.env.cfg)
         self.single_observation_shape = (self.env.obs_dim,)
         self.single_action_shape = (self.env.act_dim,)
         self.is_vector_env = True
+        self.render_mode = None
+        self.closed = False
 
     def reset(self, *, seed=None, options=None):
         e = self.env
@@ -437,5 +542,36 @@ class QuadVectorEnv:
             info["time_limit_done_n"] = time_limit_relabel(fin, rew, done, e.framework, e.x_lim)
         return (obs[0] if len(obs) == 1 else obs), rew, e.terminated.bool(), e.truncated.bool(), info
 
-    def close(self):
-        self.env.close()
+    def close(self, **kwargs):
+        if not getattr(self, "closed", True):
+            self.closed = True
+            self.env.close()
+
+    def close_extras(self, **kwargs):
+        pass
+
+
+def register_envs():
+    """gym_rotor/__init__.py:3-7 registers 'Quad-v0' (entry point QuadEnv, max_episode_steps 10000).  With gymnasium
+    importable this registers the batched counterparts under the same naming: 'Quad-v0' is left to the reference package;
+    'QuadB200-v0', 'CoupledWrapperB200-v0', 'DecoupledWrapperB200-v0' are created with
+    gymnasium.make_vec(id, num_envs=N, vectorization_mode='vector_entry_point').  Returns the registered ids
+    ([] without gymnasium)."""
+    gym = _gymnasium()
+    if gym is None:
+        return []
+    ids = []
+    for name, fw, steps in (("QuadB200-v0", "QUAD", 10000), ("CoupledWrapperB200-v0", "MONO", 4000), ("DecoupledWrapperB200-v0", "MODUL", 4000)):
+        if name not in gym.envs.registration.registry:
+            gym.envs.registration.register(id=name, vector_entry_point=_VectorEntry(fw, steps), max_episode_steps=steps)
+        ids.append(name)
+    return ids
+
+
+class _VectorEntry:
+    def __init__(self, framework, steps):
+        self.framework, self.steps = framework, steps
+
+    def __call__(self, num_envs=1, **kw):
+        kw.setdefault("max_episode_steps", self.steps)
+        return QuadVectorEnv(num_envs, framework=self.framework, **kw)

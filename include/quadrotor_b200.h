@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QR_ABI_VERSION 1
+#define QR_ABI_VERSION 2
 
 enum { QR_OK = 0, QR_ERR_INVALID = 1, QR_ERR_CUDA = 2, QR_ERR_NOMEM = 3, QR_ERR_NO_DEVICE = 4 };
 enum { QR_MODE_QUAD = 0, QR_MODE_COUPLED = 1, QR_MODE_DECOUPLED = 2 };   /* Quad-v0 | CoupledWrapper | DecoupledWrapper */
@@ -49,12 +49,15 @@ enum { QR_GOAL_EXTERNAL = 0, QR_GOAL_TRAJ_MODE0 = 1, QR_GOAL_TRAJ_HOVER = 2, QR_
        QR_GOAL_TRAJ_TAKEOFF = 5, QR_GOAL_TRAJ_LAND = 6, QR_GOAL_TRAJ_STAY = 7 };
 /* per-env status bits (the reference raises / ignores sol.status instead: coupled:63-64) */
 enum { QR_ST_NONFINITE = 1, QR_ST_TOO_SMALL_STEP = 2, QR_ST_SVD = 4 };
-/* indices into the 16-double statistics vector of qr_stats */
+/* indices into the 20-double statistics vector of qr_stats.  BENCH_REWARD: sum over env-steps of benchmark_reward_func
+ * (utils/utils.py:21-47) on the step's observation; SOLVED_AT_LIMIT: episodes that hit max_episode_steps with
+ * |ex| <= 0.03 m and reward != -1 -- what the trainer relabels done_n[0] = True (main.py:169-173). */
 enum {
     QR_STAT_EPISODES = 0, QR_STAT_RETURN0 = 1, QR_STAT_RETURN1 = 2, QR_STAT_LENGTH = 3, QR_STAT_CRASHED = 4,
     QR_STAT_TRUNCATED = 5, QR_STAT_RETURN0_SQ = 6, QR_STAT_STEPS = 7, QR_STAT_BAD_STATUS = 8, QR_STAT_NFEV = 9,
     QR_STAT_ATTEMPTS_1 = 10, QR_STAT_ATTEMPTS_2 = 11, QR_STAT_ATTEMPTS_3 = 12, QR_STAT_ATTEMPTS_4P = 13,
-    QR_STAT_REWARD0 = 14, QR_STAT_SO3_PROJECTIONS = 15, QR_NUM_STATS = 16
+    QR_STAT_REWARD0 = 14, QR_STAT_SO3_PROJECTIONS = 15, QR_STAT_BENCH_REWARD = 16, QR_STAT_SOLVED_AT_LIMIT = 17,
+    QR_NUM_STATS = 20                                                      /* 18, 19: reserved (zero) */
 };
 
 typedef struct qr_handle qr_handle;
@@ -72,7 +75,10 @@ typedef struct qr_config {
     int32_t goal_mode;          /* QR_GOAL_* */
     int32_t env_type;           /* QR_ENV_* used by in-kernel auto resets */
     int32_t max_episode_steps;  /* truncation limit (main.py:169, args_parse.py:16); 0 = none */
-    int32_t reserved0;
+    int32_t reserved0;          /* diagnostics: write nfev per env */
+    int32_t round_returns;      /* 1: running episode returns are rounded to 4 decimals after every step, as the trainer
+                                 * keeps them (main.py:180); 0: plain sums */
+    int32_t reserved1;
     double dt, g, rtol, atol;
     double x_lim, v_lim, W_lim, eIx_lim, eIb1_lim, sat_sigma, alpha, beta;
     double Cx, CIx, Cv, Cb1, CIb1, CW, Cw12, CW3;
@@ -117,9 +123,11 @@ int qr_reset(qr_handle* h, const uint8_t* mask, int env_type, void* stream);
  * For the other on-device goal modes: mark_traj_start + the first get_desired of that mode.  mask as in qr_reset. */
 int qr_init_goal(qr_handle* h, const uint8_t* mask, void* stream);
 
-/* trajectory_generator.get_desired(env.get_current_state(), mode) + env.set_goal_state, called by the trainer before
- * every step (main.py:145-147), for goal_mode HOVER / CIRCLE / EIGHT / TAKEOFF / LAND / STAY
- * (utils/trajectory_generator.py:252-505, manual fallback 232-249).  No-op for external goals and for mode 0. */
+/* One trajectory_generator.get_desired(env.get_current_state(), mode) + env.set_goal_state for goal_mode HOVER / CIRCLE /
+ * EIGHT / TAKEOFF / LAND / STAY (utils/trajectory_generator.py:252-505, manual fallback 232-249) WITHOUT stepping (it
+ * advances the trajectory clock like every get_desired call).  qr_step / qr_rollout / qr_step_host make this call
+ * themselves before every env.step, inside the step kernel, exactly where the trainer does (main.py:145-147); use this
+ * entry point only to evaluate the generator on its own.  No-op for external goals and for mode 0. */
 int qr_goal_update(qr_handle* h, void* stream);
 
 /* env.get_norm_error_state(framework) (quad.py:421-466): writes obs from the CURRENT state and goal and,
@@ -148,19 +156,21 @@ int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, fl
                uint8_t* done_out, void* stream);
 
 /* Same as qr_step with HOST buffers (pinned or pageable): copies actions host->device, steps, copies
- * obs / reward / done device->host and returns when they are valid.  This is the call the end-to-end
- * benchmark times.  Any output pointer may be NULL. */
+ * obs (dense [N][obs_dim]) / reward / done device->host and returns when they are valid.  This is the call the
+ * end-to-end benchmark times.  Any output pointer may be NULL.  The work is pipelined in chunks over two streams
+ * owned by the handle; it is ordered after everything enqueued on `stream` so far (pass the stream of the caller's
+ * earlier qr_* calls; NULL = the legacy default stream). */
 int qr_step_host(qr_handle* h, const void* actions_host, int act_dtype, float* obs_host, void* reward_host,
-                 uint8_t* done_host);
+                 uint8_t* done_host, void* stream);
 
 /* Host-layout access for C callers and tests: row-major [N][18] / [N][8] / [N][6] / [N][12] doubles
  * (env.state, env.eIx/eIb1, env.m/J/..., env.xd/vd/b1d/Wd).  NULL pointers are skipped.  Synchronous. */
 int qr_set_state_host(qr_handle* h, const double* state, const double* integ, const double* params, const double* goal);
 int qr_get_state_host(qr_handle* h, double* state, double* integ, double* params, double* goal);
 
-/* Copies the 16 statistics accumulators to host (synchronous on `stream`); reset_after != 0 zeroes them.
+/* Copies the QR_NUM_STATS statistics accumulators to host (synchronous on `stream`); reset_after != 0 zeroes them.
  * Multi-GPU callers all-reduce this vector (the only collective of the path). */
-int qr_stats(qr_handle* h, double* out16, int reset_after, void* stream);
+int qr_stats(qr_handle* h, double* out, int reset_after, void* stream);
 
 /* Number of kernels this library has launched so far in this process (for the benchmark's gpu_launches). */
 int64_t qr_launch_count(void);

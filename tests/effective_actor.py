@@ -8,8 +8,9 @@ EFFECTIVE per-layer maps were extracted once from a reference-constructed module
     block:  lin = A x + b ;  pre = lin + q(lin),  q_i = sum_jk T_ijk lin_j lin_k ;  h = sigmoid(pre[gate]) * pre[:C]
     head:   action = tanh(A_out h + b_out)
 
-This module evaluates that on device with torch (policy inference is a caller of the env path, not part of
-it; torch is the right tool for three small batched contractions).
+TEST INFRASTRUCTURE (it lives under tests/ on purpose): a torch restatement of those maps that the tests compare the
+compiled actor kernels against (qr_policy_td3 / qr_rollout with QR_ACT_POLICY, csrc/generated/actor_td3.cuh).  The
+package itself never evaluates a policy with torch/cuBLAS.
 """
 import numpy as np
 import torch

@@ -35,6 +35,7 @@ template <typename T> void fill_const(EnvConst<T>& e, const qr_config& c)   // a
     e.slope = 1.0 / (0.0 - c.reward_min); e.slope1 = 1.0 / (0.0 - c.reward_min_1); e.slope2 = 1.0 / (0.0 - c.reward_min_2);
     e.mode = c.mode; e.integrator = c.integrator; e.autoreset = c.autoreset; e.goal_mode = c.goal_mode;
     e.env_type = c.env_type; e.max_episode_steps = c.max_episode_steps; e.diagnostics = c.reserved0;
+    e.round_returns = c.round_returns;
 }
 
 template <typename T, int MODE, bool MULTI, bool GOAL1, bool POLICY = false> void lane_body(void* p) { k_step<T, MODE, MULTI, GOAL1, POLICY>(*(const StepArgs<T>*)p); }

@@ -24,7 +24,7 @@ def test_header_symbols_exported():
         assert hasattr(lib, n), "missing export %s" % n
     assert sorted(_native.EXPORTS) == names, "python binding and header disagree"
     lib.qr_abi_version.restype = ctypes.c_int
-    assert lib.qr_abi_version() == 1
+    assert lib.qr_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_config_struct_layout_matches_header():

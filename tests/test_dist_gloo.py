@@ -9,6 +9,8 @@ torch = pytest.importorskip("torch")
 import torch.distributed as dist  # noqa: E402
 import torch.multiprocessing as mp  # noqa: E402
 
+from gym_rotor_b200._native import NUM_STATS  # noqa: E402
+
 
 def test_shard_range_partitions_exactly():
     from gym_rotor_b200.dist import shard_range
@@ -33,7 +35,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from gym_rotor_b200.dist import reduce_stats_tensor, shard_range, summarize
     lo, hi = shard_range(1000, rank, world)
-    s = torch.zeros(16, dtype=torch.float64)
+    s = torch.zeros(NUM_STATS, dtype=torch.float64)
     s[0] = hi - lo                 # episodes
     s[1] = float(sum(range(lo, hi)))   # sum of returns
     s[3] = 10.0 * (hi - lo)
@@ -58,5 +60,5 @@ def test_reduce_stats_rejects_wrong_shape():
     from gym_rotor_b200.dist import reduce_stats_tensor
     with pytest.raises(ValueError):
         reduce_stats_tensor(torch.zeros(8, dtype=torch.float64))
-    s = torch.arange(16, dtype=torch.float64)
+    s = torch.arange(NUM_STATS, dtype=torch.float64)
     assert torch.equal(reduce_stats_tensor(s.clone()), s)   # no process group: identity

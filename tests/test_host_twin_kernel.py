@@ -88,7 +88,7 @@ class HostEnv:
         self.terminated = np.zeros(n, np.uint8); self.truncated = np.zeros(n, np.uint8)
         self.nfev = np.zeros(n, np.int32); self.status = np.zeros(n, np.uint8)
         self.ep_return = np.zeros((2, n), T); self.ep_length = np.zeros(n, np.int32); self.ep_index = np.zeros(n, np.uint32)
-        self.stats = np.zeros(16, np.float64)
+        self.stats = np.zeros(20, np.float64)   # QR_NUM_STATS
 
     def set_state(self, st, ig, par, goal):          # [n,18] [n,8] [n,6] [n,12] like vec_env.set_state
         self.state[:] = np.asarray(st).T; self.integ[:] = np.asarray(ig).T
@@ -484,3 +484,59 @@ def test_kernel_fp64_free_running_vs_c_oracle(libs):
             break
         assert _relerr(env.state.T[alive], st_o[alive]) <= 1e-9, t
     assert t > 50
+
+
+@pytest.mark.parametrize("gm", [2, 3, 4, 5])
+def test_kernel_step_evaluates_the_trajectory_goal_itself(libs, gm):
+    """Goal modes hover / circle / eight / take-off: the step kernel calls get_desired + set_goal_state on the pre-step state
+    before every env.step (main.py:145-147).  Single-step and multi-step launches == k_goal_update followed by a step that
+    takes the goal as an external one, step by step: state, integrals, goal, trajectory state, observations, rewards."""
+    K, F = libs
+    n, steps = 70, 6
+    kw = dict(n_envs=n, seed=11, goal_mode=gm)
+    ea, eb, ec = (HostEnv(K, _config(1, True, **kw), warps=w) for w in (2, 3, 1))
+    for e in (ea, eb, ec):
+        _reset_all(F, e.cfg, e)
+        e.companion("init_goal")
+    rng = np.random.default_rng(2)
+    acts = rng.uniform(-0.3, 0.3, (steps, n, 4))
+    obs_r, rew_r, _ = ec.launch(acts, n_steps=steps, store=True)       # goal generated inside a multi-step launch
+    for k in range(steps):
+        ea.launch(acts[k])                                             # ... inside single-step launches
+        eb.companion("goal_update")                                    # ... by the companion kernel, then an external-goal step
+        eb.cfg.goal_mode = 0
+        eb.launch(acts[k])
+        eb.cfg.goal_mode = gm
+        for name in ("state", "integ", "goal", "traj", "obs", "reward", "done"):
+            assert np.array_equal(getattr(ea, name), getattr(eb, name)), (k, name)
+        assert np.array_equal(obs_r[k], ea.obs) and np.array_equal(rew_r[k], ea.reward), k
+    for name in ("state", "integ", "goal", "traj"):
+        assert np.array_equal(getattr(ec, name), getattr(ea, name)), name
+    assert np.abs(ea.goal[0:3]).max() > 0 and ea.traj[0].min() > 0     # a moving position command, clocks advanced
+
+
+def test_kernel_benchmark_reward_solved_count_and_rounded_returns(libs):
+    """Statistics 16 / 17 (sum of benchmark_reward_func over env-steps, utils/utils.py:21-47; episodes the trainer relabels
+    as solved at the time limit, main.py:169-173) and the trainer's 4-decimal running return (main.py:180, round_returns)."""
+    K, F = libs
+    n, steps = 64, 3
+    cfg = _config(1, True, n_envs=n, seed=4, goal_mode=0, max_episode_steps=steps, round_returns=1)
+    env = HostEnv(K, cfg, warps=2)
+    st, ig, par, gl = _reset_all(F, cfg, env)
+    st[: n // 2, 0:6] = 0.0                                  # half of the envs sit at the goal: x = xd = 0, v = 0
+    st[: n // 2, 6:15] = np.eye(3).reshape(-1); st[: n // 2, 15:18] = 0.0
+    gl[:] = 0.0; gl[:, 6] = 1.0
+    env.set_state(st, ig, par, gl)
+    rng = np.random.default_rng(6)
+    br_sum, ret = 0.0, np.zeros(n)
+    for k in range(steps):
+        act = rng.uniform(-0.05, 0.05, (n, 4)); act[:, 0] = -0.06
+        env.launch(act)
+        o = env.obs.astype(np.float64)
+        r = -np.linalg.norm(o[:, 0:3] * 1.0, axis=1) - np.abs(o[:, 18] * np.pi)
+        br_sum += np.interp(r, [-2.0, 0.0], [0.0, 1.0]).sum()
+        ret = np.array([float("{:.4f}".format(a + b)) for a, b in zip(ret, env.reward[:, 0])])
+        assert np.array_equal(env.ep_return[0], ret), k
+    assert abs(env.stats[16] - br_sum) < 1e-4 * br_sum
+    solved = (np.abs(env.obs[:, 0:3].astype(np.float64)) <= 0.03).all(axis=1) & (env.reward[:, 0] != -1.0)
+    assert env.truncated.all() and env.stats[17] == solved.sum() and 0 < solved.sum() < n

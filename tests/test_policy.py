@@ -11,7 +11,7 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.mark.parametrize("tag,agents", [("mono", 1), ("modul", 2)])
 def test_effective_actor_matches_reference_outputs(tag, agents):
-    from gym_rotor_b200.policy import EffectiveActor
+    from effective_actor import EffectiveActor
     z = np.load(os.path.join(G, "policy_td3_%s.npz" % tag))
     for i in range(agents):
         pi = EffectiveActor(z, agent=i, device="cpu")
@@ -29,7 +29,7 @@ def test_policy_in_the_loop_reproduces_reference_eval_episode(fw, tag, A):
     """BASELINE config 5 at N=1 scale: fp64 env on the GPU + the extracted actor, 1000 steps, against the episode the
     reference flew with the same checkpoint (return 989.8 MONO; 992.6 / 998.0 MODUL)."""
     from gym_rotor_b200 import vec_env
-    from gym_rotor_b200.policy import EffectiveActor
+    from effective_actor import EffectiveActor
     ep = np.load(os.path.join(G, "eval_%s.npz" % tag))
     z = np.load(os.path.join(G, "policy_td3_%s.npz" % tag))
     pis = [EffectiveActor(z, agent=i) for i in range(len(A))]
