@@ -16,9 +16,11 @@ namespace qr {
 // ---- arithmetic that must NOT be contracted into FMAs (numpy evaluates these op by op) --------------
 template <typename T> struct rn;
 template <> struct rn<float> {
-    static QR_DEV float mul(float a, float b) { return __fmul_rn(a, b); }
-    static QR_DEV float add(float a, float b) { return __fadd_rn(a, b); }
-    static QR_DEV float sub(float a, float b) { return __fsub_rn(a, b); }
+    // float32 mode is not the bit-parity mode (bar: 1e-5 of the reference): plain operators, so that the compiler contracts
+    // multiply-add chains into FMAs; the float64 instantiation below keeps numpy's op-by-op roundings
+    static QR_DEV float mul(float a, float b) { return a * b; }
+    static QR_DEV float add(float a, float b) { return a + b; }
+    static QR_DEV float sub(float a, float b) { return a - b; }
     static QR_DEV float div(float a, float b) { return __fdiv_rn(a, b); }
     // division by a launch constant: multiply by its host-computed reciprocal (float32 mode is not the
     // bit-parity mode; the float64 instantiation below keeps numpy's exact quotient)
@@ -47,10 +49,12 @@ struct Philox {
     uint32_t k0, k1;
     // rolled on purpose: resets and in-kernel action draws sit in divergent, once-per-episode paths where
     // code size (instruction cache) matters more than the ten-round latency
-    QR_DEV void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) const
+    QR_DEV void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) const { run<false>(c0, c1, c2, c3, out); }
+    // UNROLLED: the per-step action draw of the synthetic workload sits in the hot loop (3.4 % of its instructions when rolled)
+    template <bool UNROLLED> QR_DEV void run(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) const
     {
         uint32_t a = k0, b = k1;
-#pragma unroll 1
+#pragma unroll(UNROLLED ? 10 : 1)
         for (int r = 0; r < 10; ++r) {
             uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
             uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -273,6 +277,20 @@ QR_DEV double interp01(double r, double rmin, double slope)
     return __dadd_rn(__dmul_rn(slope, __dsub_rn(r, rmin)), 0.0);
 }
 
+// float32 mode: the same interpolation in float32 (no trip through the FP64 pipe)
+QR_DEV float interp01f(float r, float rmin, float slope)
+{
+    if (r != r) return r;
+    if (r <= rmin) return 0.0f;
+    if (r >= 0.0f) return 1.0f;
+    return slope * (r - rmin);
+}
+template <typename T> QR_DEV double interp01t(float r, double rmin, double slope)
+{
+    if (sizeof(T) == 8) return interp01((double)r, rmin, slope);
+    return (double)interp01f(r, (float)rmin, (float)slope);
+}
+
 template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float* o, double* rew, int* dn, const int mode)
 {
     dn[0] = 0; dn[1] = 0;
@@ -285,7 +303,7 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
 #pragma unroll
         for (int i = 0; i < 3; ++i)
             if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[20 + i]) >= 1.0f) dn[0] = 1;
-        rew[0] = dn[0] ? -1.0 : interp01((double)r, c.rmin, c.slope);
+        rew[0] = dn[0] ? -1.0 : interp01t<T>(r, c.rmin, c.slope);
         rew[1] = 0.0;
     } else {
         float rx = __fmul_rn(c.nCx, norm2sq_f32<sizeof(T) == 8>(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32<sizeof(T) == 8>(o + 3));
@@ -298,8 +316,8 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
         for (int i = 0; i < 3; ++i)
             if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[12 + i]) >= 1.0f) dn[0] = 1;
         if (a2 >= 1.0f) dn[1] = 1;
-        rew[0] = dn[0] ? -1.0 : interp01((double)r1, c.rmin1, c.slope1);
-        rew[1] = dn[1] ? -1.0 : interp01((double)r2, c.rmin2, c.slope2);
+        rew[0] = dn[0] ? -1.0 : interp01t<T>(r1, c.rmin1, c.slope1);
+        rew[1] = dn[1] ? -1.0 : interp01t<T>(r2, c.rmin2, c.slope2);
     }
 }
 

@@ -264,8 +264,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     if (LOCKSTEP != 0) {
         const int nw = (int)(blockDim.x >> 5);
         if (LOCKSTEP > 0) {
-            grp_id = warp / LOCKSTEP;
-            grp_threads = 32 * min(LOCKSTEP, nw - grp_id * LOCKSTEP);
+            constexpr int G_ = LOCKSTEP > 0 ? LOCKSTEP : 1;
+            grp_id = warp / G_;
+            grp_threads = 32 * min(G_, nw - grp_id * G_);
         } else {
             grp_id = warp & 3;
             grp_threads = 32 * ((nw - grp_id + 3) >> 2);
@@ -796,8 +797,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 cp_async_wait_all();
                 const uint32_t ep_idx = (uint32_t)stash_i32(sh, S_IDX);
                 const int ep_len = stash_i32(sh, S_LEN);
-                ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len, rnd);
-                if (A == 5) ph((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len + 1u, rnd + 4);
+                ph.template run<true>((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len, rnd);
+                if (A == 5) ph.template run<true>((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len + 1u, rnd + 4);
 #pragma unroll
                 for (int i = 0; i < A; ++i) act[i] = (T)(2.0 * u01(rnd[i]) - 1.0);
                 act_f32 = false;
