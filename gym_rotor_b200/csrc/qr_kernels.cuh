@@ -557,8 +557,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 const int att = (nf - 2) / 12;
                 const int s_nfev = __reduce_add_sync(FULL, nf);
                 const int s_proj = __reduce_add_sync(FULL, nproj);
-                const unsigned m1 = __ballot_sync(FULL, fin && att == 1), m2 = __ballot_sync(FULL, fin && att == 2);
-                const unsigned m3 = __ballot_sync(FULL, fin && att == 3), m4 = __ballot_sync(FULL, fin && att >= 4);
+                // attempt histogram: with diagnostics only (kernel-uniform); the mean is always available from the nfev sum (2 + 12 per attempt)
+                unsigned m1 = 0, m2 = 0, m3 = 0, m4 = 0;
+                if (c.diagnostics) {
+                    m1 = __ballot_sync(FULL, fin && att == 1); m2 = __ballot_sync(FULL, fin && att == 2);
+                    m3 = __ballot_sync(FULL, fin && att == 3); m4 = __ballot_sync(FULL, fin && att >= 4);
+                }
                 const unsigned mbad = __ballot_sync(FULL, fin && st != 0);
                 const float s_rew = warp_sum_f(rew0f);
                 const float s_brew = (MODE != 0) ? warp_sum_f(brew) : 0.f;
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (lane == 0) {
                     if (MODE != 0) { ws[16] += (double)s_brew; if (msolved) ws[17] += (double)__popc(msolved); }
                     ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev; ws[15] += (double)s_proj;
-                    ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
+                    if (c.diagnostics) { ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4); }
                     ws[8] += (double)__popc(mbad); ws[14] += (double)s_rew;
                 }
                 if (mres) {   // once per episode
@@ -738,10 +742,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const bool staged_act = a.actions && (a.act_f32 || sizeof(T) == 8);   // what A0 can stage (kernel-uniform)
             const bool staged = MULTI ? fresh : true;   // adopted in this round's A2: action, parameters and b1d were fetched ahead into the stash
             fresh = false;
+            if (staged) cp_async_wait_group<1>();   // everything but A2's group (end-of-step values, not needed yet)
+            // the parameters stay in the landing zone of the stash for as long as the env stays in this lane (only a lane that is
+            // idle or on its last sub-step is handed a next env, A0): later sub-steps read them from there, not from HBM
+            p_m = sh[(S_PAR + 0) * 32]; p_J1 = sh[(S_PAR + 2) * 32]; p_J3 = sh[(S_PAR + 3) * 32]; p_ctw = sh[(S_PAR + 5) * 32];
+            if (MODE == 0) { p_d = sh[(S_PAR + 1) * 32]; p_ctf = sh[(S_PAR + 4) * 32]; }
             if (staged) {
-                cp_async_wait_group<1>();   // everything but A2's group (end-of-step values, not needed yet)
-                p_m = sh[(S_PAR + 0) * 32]; p_J1 = sh[(S_PAR + 2) * 32]; p_J3 = sh[(S_PAR + 3) * 32]; p_ctw = sh[(S_PAR + 5) * 32];
-                if (MODE == 0) { p_d = sh[(S_PAR + 1) * 32]; p_ctf = sh[(S_PAR + 4) * 32]; }
                 if (staged_act) {
 #pragma unroll
                     for (int i = 0; i < A; ++i)
@@ -751,13 +757,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 #pragma unroll
                     for (int i = 0; i < 3; ++i) b1d[i] = sh[(S_NB1D + i) * 32];
                 }
-            } else {
-                p_m = a.params[0 * N + e]; p_J1 = a.params[2 * N + e]; p_J3 = a.params[3 * N + e]; p_ctw = a.params[5 * N + e];
-                if (MODE == 0) { p_d = a.params[1 * N + e]; p_ctf = a.params[4 * N + e]; }
-                if (GOAL1) {
+            } else if (GOAL1) {   // b1d of the step before (constant within an episode in mode 0), kept for the observation
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) b1d[i] = a.goal[(6 + i) * N + e];
-                }
+                for (int i = 0; i < 3; ++i) b1d[i] = sh[(S_B1D + i) * 32];
             }
             if (a.actions && !(staged && staged_act)) {
                 const int64_t base = ((int64_t)k * N + e) * A;
@@ -800,7 +802,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 ph.template run<true>((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len, rnd);
                 if (A == 5) ph.template run<true>((uint32_t)gid, (uint32_t)(gid >> 32), ep_idx, QR_DOMAIN_ACTION + 2u * (uint32_t)ep_len + 1u, rnd + 4);
 #pragma unroll
-                for (int i = 0; i < A; ++i) act[i] = (T)(2.0 * u01(rnd[i]) - 1.0);
+                for (int i = 0; i < A; ++i) act[i] = (sizeof(T) == 8) ? (T)(2.0 * u01(rnd[i]) - 1.0) : (T)2 * u01t<T>(rnd[i]) - (T)1;   // U(-1, 1)
                 act_f32 = false;
             }
             // state_decomposition of the incoming state: get_desired (trajectory_generator.py:115) and
@@ -848,7 +850,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             T f, M[3];
             action_to_fM<T>(r, c, act, act_f32, f, M, MODE);
             {
-                const T rm = (T)1 / p_m, rJ1 = (T)1 / p_J1, rJ3 = (T)1 / p_J3;   // inv(J) as the reference forms it (quad.py:329)
+                // inv(J) as the reference forms it (quad.py:329); float32 mode: MUFU reciprocals (<= 1 ulp)
+                const T rm = num<T>::recip(p_m), rJ1 = num<T>::recip(p_J1), rJ3 = num<T>::recip(p_J3);
                 d.fm = f * rm; d.g = c.g;
                 d.Mi0 = M[0] * rJ1; d.Mi1 = M[1] * rJ1;
                 d.kw0 = (p_J1 - p_J3) * rJ1; d.kw1 = (p_J3 - p_J1) * rJ1;

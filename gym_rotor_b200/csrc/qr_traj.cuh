@@ -21,7 +21,15 @@ template <> QR_DEV double exp_t<double>(double a) { return exp(a); }
 template <> QR_DEV float exp_t<float>(float a) { return expf(a); }
 template <typename T> QR_DEV void sincos_acc(T a, T* s, T* c);
 template <> QR_DEV void sincos_acc<double>(double a, double* s, double* c) { sincos(a, s, c); }
-template <> QR_DEV void sincos_acc<float>(float a, float* s, float* c) { sincosf(a, s, c); }
+// float32 mode: the arguments (w t + theta0) stay within a few tens of radians, so a two-constant Cody-Waite reduction to
+// [-pi, pi] followed by the MUFU pair (abs error ~4e-7) replaces sincosf and its Payne-Hanek slow path
+template <> QR_DEV void sincos_acc<float>(float a, float* s, float* c)
+{
+    const float k = rintf(a * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, a);
+    r = fmaf(k, 1.7484555e-7f, r);   // 2 pi = 6.2831854820251465 - 1.7484555e-7
+    __sincosf(r, s, c);
+}
 
 // mark_traj_start: clock and flags to zero, initial position / heading from the state handed in
 template <typename T> QR_DEV void traj_start(const T* x, const T* R_so3, T* ts)
@@ -45,13 +53,13 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
     const T PI = (T)3.14159265358979323846;
     T* xd = goal; T* vd = goal + 3; T* b1d = goal + 6; T* Wd = goal + 9;
     int flags = (int)ts[1];
-    const T th_cur = N::atan2(R[1], R[0]);   // get_current_b1
+    // get_current_b1 = atan2(R[1], R[0]) is only needed when a trajectory (or the manual mode after it) starts: evaluated there
     T sn, cs;
     if (flags & 2) {   // manual(): calculate_desired returns before the Wd block
         if (!(flags & 4)) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; }
-            ts[5] = th_cur;
+            ts[5] = N::atan2(R[1], R[0]);
             flags |= 4;
         }
         vd[0] = vd[1] = vd[2] = 0;
@@ -63,7 +71,7 @@ QR_DEV void traj_desired(int mode, const T* x, const T* v, const T* R, const T* 
     if (!(flags & 1)) {   // set_desired_states_to_current + per-mode start
 #pragma unroll
         for (int i = 0; i < 3; ++i) { xd[i] = x[i]; vd[i] = v[i]; ts[2 + i] = x[i]; }
-        sincos_acc<T>(th_cur, &sn, &cs);
+        sincos_acc<T>(N::atan2(R[1], R[0]), &sn, &cs);
         b1d[0] = cs; b1d[1] = sn; b1d[2] = 0;
         flags |= 1;
         if (mode == 1) {

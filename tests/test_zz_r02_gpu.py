@@ -67,7 +67,7 @@ def test_decoupled_full_size_invariants_and_env_swap():
         assert torch.equal(getattr(ea, name), getattr(eb, name)), name
     sa, sb = ea.stats(), eb.stats()
     assert sa[7] == sb[7] == K * n and sa[0] == sb[0] >= 2 * n and sa[3] == sb[3] and sa[5] == sb[5]
-    assert abs(sa[10:14].sum() - sa[7]) < 0.5 and int(ea.status.max()) == 0
+    assert sa[9] == sb[9] >= 14 * sa[7] and sa[10:14].sum() == 0 and int(ea.status.max()) == 0   # nfev = 2 + 12 per attempt; no histogram without diagnostics
     o = ea.obs
     assert bool(torch.isfinite(o).all()) and bool((o[:, 0:3].abs() < 1).all()) and bool((o[:, 6:9].abs() < 1).all())
     R = ea.state_soa[6:15].t().reshape(n, 3, 3)
