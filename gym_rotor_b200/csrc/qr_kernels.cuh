@@ -32,6 +32,12 @@ __host__ __device__ constexpr int obs_stride_of(int O) { return (O + 3) & ~3; }
 #define QR_LOCKSTEP_MULTI 0    // multi-step launches (long-running: the warps of a block drift fully out of phase)
 #endif
 #define QR_NSTATS 20   // QR_NUM_STATS of include/quadrotor_b200.h
+// 1: the next env's state is fetched global -> shared (cp.async into the park area of the stage storage, free until the reset
+// section) instead of into dead registers, so that no scoreboard of the end-of-step code is shared with loads on their way to
+// HBM (+2 % at one step per launch, profiles/r02/r02p_ab.txt; 0: round 1's loads into the dead registers of K0 and d)
+#ifndef QR_PREFETCH_KS
+#define QR_PREFETCH_KS 1
+#endif
 #ifndef QR_KS_SLOTS_F32
 #define QR_KS_SLOTS_F32 6   // float32 keeps K2..K8 in slots 0..5 (qr_dop853.cuh); with 6 the block fits the 196 KB shared-memory configuration (60 KB of L1 instead of 28: +5 %, profiles/r02/r02e_ab.txt)
 #endif
@@ -308,6 +314,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     constexpr int S_ACT = 18, S_PAR = 23, S_NB1D = 29;   // next env, fetched ahead: action (<= 5), parameters (6), b1d (3)
     bool has_next = false;   // K0 / d hold the NEXT env's state (loads in flight), the stash its action etc.
     bool fresh = false;      // the env was adopted in this round's A2: its action / parameters / b1d are in the stash
+    bool r_ok = false;       // multi-step launches: the attitude passed ensure_SO3 in the observation that ended the previous sub-step
     int64_t e_next = 0;
     int k_next = 0;          // multi-step launches: the sub-step at which the fetched env goes on (a reset env resumes mid-rollout)
 #pragma unroll
@@ -325,9 +332,9 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         // =============================== phase A ===============================
         const unsigned finmask = __ballot_sync(FULL, fin);
         // ---- A0: lanes that are idle, or about to release their env, are given the next env of the warp's sequence
-        // NOW and start fetching it: the state into the (dead) registers of K0 and d, action / parameters / goal
-        // into the stash with cp.async.  The round trip to HBM overlaps the end-of-step work below instead of
-        // stalling the start of the next step.
+        // NOW and start fetching it with cp.async (no register in between): the state into the park area of the stage
+        // storage, action / parameters / goal into the stash.  The round trip to HBM overlaps the end-of-step work
+        // below instead of stalling the start of the next step.
         {
             const bool leaving = fin && (k == NS - 1);
             const unsigned need = __ballot_sync(FULL, (!busy || leaving) && !has_next);
@@ -364,10 +371,15 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     // K0 and d are dead for a lane that is idle or has finished its step (A1 only reads ode's counters)
                     // (K0 is kept in the integrator's internal order, qr_dop853.cuh: the fetched state lands in the
                     //  matching positions, so that y and K0 agree on which components form a register pair)
+#if QR_PREFETCH_KS
+#pragma unroll
+                    for (int i = 0; i < 18; ++i) cp_async<sizeof(T)>(ks + 1024 + i * 32 + lane, a.state + i * N + ee);
+#else
                     d.fm = a.state[0 * N + ee]; d.g = a.state[1 * N + ee]; d.Mi0 = a.state[2 * N + ee];
 #pragma unroll
                     for (int i = 0; i < 14; ++i) K0[zof(i)] = a.state[(3 + i) * N + ee];
                     d.Mi1 = a.state[17 * N + ee];
+#endif
                     if (a.actions) {
                         if (a.act_f32) {
                             const float* p = (const float*)a.actions + ((int64_t)kk * N + ee) * A;
@@ -444,6 +456,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 } else {
                     int fl = norm_error_state<T>(r, c, o, MODE);
                     if (fl & 2) st |= 4;
+                    if (MULTI) r_ok = (fl == 0);
                     reward_done<T>(c, o, rew, dn, MODE);
                 }
 #pragma unroll
@@ -453,8 +466,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 // full sectors; measured 5 % faster than a general coalescing copy through shared memory).  When the
                 // whole warp finishes 32 consecutive envs together (`coop`: the lock-step regime of a trained
                 // policy), the rows go through a shared tile and leave as 16-byte stores of one contiguous block.
-                obs1 = a.obs_roll ? a.obs_roll + ((int64_t)k * N + e) * O : ((last || POLICY) ? a.obs + e * OS : nullptr);
-                obs2 = (a.obs_roll && (last || POLICY)) ? a.obs + e * OS : nullptr;   // POLICY: the actor reads a.obs at the next sub-step
+                if (a.obs_roll) {   // kernel-uniform: caller's rollout storage (dense rows), plus the handle's row where it is read back
+                    obs1 = a.obs_roll + ((int64_t)k * N + e) * O;
+                    if (last || POLICY) obs2 = a.obs + e * OS;   // POLICY: the actor reads a.obs at the next sub-step
+                } else if (last || POLICY) obs1 = a.obs + e * OS;
                 if (coop) {
                     float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
 #pragma unroll
@@ -502,12 +517,18 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     solved = trunc && fabsf(ex0) <= 0.03f && fabsf(ex1) <= 0.03f && fabsf(ex2) <= 0.03f && rew[0] != -1.0;
                 }
                 // per-step scalar outputs
-                T* rw = a.reward_roll ? a.reward_roll + ((int64_t)k * N + e) * G : (last ? a.reward + e * G : nullptr);
-                uint8_t* dd = a.done_roll ? a.done_roll + ((int64_t)k * N + e) * G : (last ? a.done + e * G : nullptr);
-                if (rw) { rw[0] = (T)rew[0]; if (G == 2) rw[1] = (T)rew[1]; }
-                if (dd) { dd[0] = (uint8_t)dn[0]; if (G == 2) dd[1] = (uint8_t)dn[1]; }
-                if (a.reward_roll && last) { a.reward[e * G] = (T)rew[0]; if (G == 2) a.reward[e * G + 1] = (T)rew[1]; }
-                if (a.done_roll && last) { a.done[e * G] = (uint8_t)dn[0]; if (G == 2) a.done[e * G + 1] = (uint8_t)dn[1]; }
+                if (a.reward_roll) {   // (kernel-uniform)
+                    T* rw = a.reward_roll + ((int64_t)k * N + e) * G;
+                    rw[0] = (T)rew[0]; if (G == 2) rw[1] = (T)rew[1];
+                }
+                if (a.done_roll) {
+                    uint8_t* dd = a.done_roll + ((int64_t)k * N + e) * G;
+                    dd[0] = (uint8_t)dn[0]; if (G == 2) dd[1] = (uint8_t)dn[1];
+                }
+                if (last) {
+                    a.reward[e * G] = (T)rew[0]; if (G == 2) a.reward[e * G + 1] = (T)rew[1];
+                    a.done[e * G] = (uint8_t)dn[0]; if (G == 2) a.done[e * G + 1] = (uint8_t)dn[1];
+                }
                 if (last) { a.terminated[e] = (uint8_t)term; a.truncated[e] = (uint8_t)trunc; }
                 if (c.diagnostics && last) a.nfev[e] = nf;
                 if (st) a.status[e] |= (uint8_t)st;
@@ -621,9 +642,21 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         if (has_next && !busy) {
             has_next = false;
             e = e_next; k = MULTI ? k_next : 0; busy = true; need_init = true; if (MULTI) fresh = true;
+#if QR_PREFETCH_KS
+            cp_async_wait_all();   // this round's A0 group, issued a whole end-of-step ago
+            {
+                const T* pf = ks + 1024 + lane;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) x[i] = pf[i * 32];
+#pragma unroll
+                for (int i = 0; i < 14; ++i) y[i] = pf[(3 + i) * 32];
+                W3 = pf[17 * 32];
+            }
+#else
             x[0] = d.fm; x[1] = d.g; x[2] = d.Mi0; W3 = d.Mi1;
 #pragma unroll
             for (int i = 0; i < 14; ++i) y[i] = K0[zof(i)];
+#endif
             // end-of-step values go global -> stash without passing through registers (needed when the step ends)
 #pragma unroll
             for (int i = 0; i < 8; ++i) cp_async<sizeof(T)>(sh + (S_I + i) * 32, a.integ + i * N + e);
@@ -673,7 +706,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 pk[39 * 32] = ode.t; pk[40 * 32] = ode.h_abs;
                 QR_PKI(41) = ode.rejected; QR_PKI(42) = ode.nfev; QR_PKI(43) = ode.status; QR_PKI(44) = ode.nproj; QR_PKI(45) = ode.checked;
                 if (MULTI) QR_PKI(46) = k;
-                QR_PKI(47) = (int)busy | ((int)fin << 1) | ((int)need_init << 2) | ((int)has_next << 3) | ((int)exhausted << 4) | ((int)(MULTI && fresh) << 5);
+                QR_PKI(47) = (int)busy | ((int)fin << 1) | ((int)need_init << 2) | ((int)has_next << 3) | ((int)exhausted << 4) | ((int)(MULTI && fresh) << 5) | ((int)(MULTI && r_ok) << 6);
                 QR_PKI(48) = (int32_t)(uint32_t)e; QR_PKI(49) = (int32_t)(e >> 32);
                 QR_PKI(50) = (int32_t)(uint32_t)e_next; QR_PKI(51) = (int32_t)(e_next >> 32);
                 QR_PKI(52) = (int32_t)(uint32_t)tile_base; QR_PKI(53) = (int32_t)(tile_base >> 32);
@@ -695,7 +728,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (MULTI) k = QR_PKI(46);
                 {
                     const int fl = QR_PKI(47);
-                    busy = fl & 1; fin = (fl >> 1) & 1; need_init = (fl >> 2) & 1; has_next = (fl >> 3) & 1; exhausted = (fl >> 4) & 1; fresh = (fl >> 5) & 1;
+                    busy = fl & 1; fin = (fl >> 1) & 1; need_init = (fl >> 2) & 1; has_next = (fl >> 3) & 1; exhausted = (fl >> 4) & 1; fresh = (fl >> 5) & 1; r_ok = (fl >> 6) & 1;
                 }
                 e = (int64_t)(((uint64_t)(uint32_t)QR_PKI(49) << 32) | (uint32_t)QR_PKI(48));
                 e_next = (int64_t)(((uint64_t)(uint32_t)QR_PKI(51) << 32) | (uint32_t)QR_PKI(50));
@@ -807,7 +840,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             }
             // state_decomposition of the incoming state: get_desired (trajectory_generator.py:115) and
             // observation_wrapper (coupled:58) both run ensure_SO3 on the same R; once is enough
-            int fl = ensure_so3<T>(y + 3);
+            // ... and in a multi-step launch the observation that ended the previous sub-step (get_norm_error_state ->
+            // state_normalization) has just run the same test on the same matrix: if it passed there, it passes here
+            int fl = 0;
+            if (!(MULTI && MODE != 0 && !staged && r_ok)) fl = ensure_so3<T>(y + 3);
             EnvRegs<T> r;
 #pragma unroll
             for (int i = 0; i < 3; ++i) r.x[i] = x[i];
