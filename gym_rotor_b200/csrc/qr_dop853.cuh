@@ -321,6 +321,13 @@ template <typename T> QR_DEV bool so3_ok_z(const T* z, T* mx = nullptr)
     const T cy = N::fma(z[7], z[4], -(z[2] * z[8]));
     const T cz = N::fma(z[2], z[5], -(z[3] * z[4]));
     const T dm1 = N::fma(z[0], cx, N::fma(z[1], cy, N::fma(z[6], cz, (T)-1)));
+    if (mx && sizeof(T) == 8) {
+        // float64 (no NaN-propagating 3-input maximum there): the seven comparisons per stage, folded into the first maximum
+        const bool ok = (N::abs(e00) <= tol + tol) & (N::abs(e11) <= tol + tol) & (N::abs(e22) <= tol + tol) & (N::abs(e01) <= tol) &
+                        (N::abs(e02) <= tol) & (N::abs(e12) <= tol) & (N::abs(dm1) <= (T)1e-8 + tol);
+        mx[0] = ok ? mx[0] : N::inf();
+        return true;
+    }
     if (mx) {
         // speculative stages (stage_finish): the seven defects only feed three running maxima (diagonal, off-diagonal,
         // determinant; NaN-propagating), compared once at the end of the attempt instead of seven times per stage

@@ -34,7 +34,8 @@ __host__ __device__ constexpr int obs_stride_of(int O) { return (O + 3) & ~3; }
 #define QR_NSTATS 20   // QR_NUM_STATS of include/quadrotor_b200.h
 // 1: the next env's state is fetched global -> shared (cp.async into the park area of the stage storage, free until the reset
 // section) instead of into dead registers, so that no scoreboard of the end-of-step code is shared with loads on their way to
-// HBM (+2 % at one step per launch, profiles/r02/r02p_ab.txt; 0: round 1's loads into the dead registers of K0 and d)
+// HBM (+2 % at one step per launch, profiles/r02/r02p_ab.txt; 0: round 1's loads into the dead registers of K0 and d, which
+// the float64 kernels keep: r02r_f64_variants.txt)
 #ifndef QR_PREFETCH_KS
 #define QR_PREFETCH_KS 1
 #endif
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     const int64_t N = a.n;
     const int NS = MULTI ? a.n_steps : 1;   // single-step kernels: the sub-step counter k folds to the constant 0
     constexpr int LOCKSTEP = MULTI ? QR_LOCKSTEP_MULTI : QR_LOCKSTEP;
+    constexpr bool PREFETCH_KS = QR_PREFETCH_KS != 0 && sizeof(T) == 4;   // float64: the loads into dead registers measured 4 % faster
     int grp_id = 0, grp_threads = 0;   // lock-step group of this warp: named barrier (1 + group), threads in it
     if (LOCKSTEP != 0) {
         const int nw = (int)(blockDim.x >> 5);
@@ -371,15 +373,15 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     // K0 and d are dead for a lane that is idle or has finished its step (A1 only reads ode's counters)
                     // (K0 is kept in the integrator's internal order, qr_dop853.cuh: the fetched state lands in the
                     //  matching positions, so that y and K0 agree on which components form a register pair)
-#if QR_PREFETCH_KS
+                    if (PREFETCH_KS) {
 #pragma unroll
-                    for (int i = 0; i < 18; ++i) cp_async<sizeof(T)>(ks + 1024 + i * 32 + lane, a.state + i * N + ee);
-#else
-                    d.fm = a.state[0 * N + ee]; d.g = a.state[1 * N + ee]; d.Mi0 = a.state[2 * N + ee];
+                        for (int i = 0; i < 18; ++i) cp_async<sizeof(T)>(ks + 1024 + i * 32 + lane, a.state + i * N + ee);
+                    } else {
+                        d.fm = a.state[0 * N + ee]; d.g = a.state[1 * N + ee]; d.Mi0 = a.state[2 * N + ee];
 #pragma unroll
-                    for (int i = 0; i < 14; ++i) K0[zof(i)] = a.state[(3 + i) * N + ee];
-                    d.Mi1 = a.state[17 * N + ee];
-#endif
+                        for (int i = 0; i < 14; ++i) K0[zof(i)] = a.state[(3 + i) * N + ee];
+                        d.Mi1 = a.state[17 * N + ee];
+                    }
                     if (a.actions) {
                         if (a.act_f32) {
                             const float* p = (const float*)a.actions + ((int64_t)kk * N + ee) * A;
@@ -642,21 +644,19 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         if (has_next && !busy) {
             has_next = false;
             e = e_next; k = MULTI ? k_next : 0; busy = true; need_init = true; if (MULTI) fresh = true;
-#if QR_PREFETCH_KS
-            cp_async_wait_all();   // this round's A0 group, issued a whole end-of-step ago
-            {
+            if (PREFETCH_KS) {
+                cp_async_wait_all();   // this round's A0 group, issued a whole end-of-step ago
                 const T* pf = ks + 1024 + lane;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) x[i] = pf[i * 32];
 #pragma unroll
                 for (int i = 0; i < 14; ++i) y[i] = pf[(3 + i) * 32];
                 W3 = pf[17 * 32];
-            }
-#else
-            x[0] = d.fm; x[1] = d.g; x[2] = d.Mi0; W3 = d.Mi1;
+            } else {
+                x[0] = d.fm; x[1] = d.g; x[2] = d.Mi0; W3 = d.Mi1;
 #pragma unroll
-            for (int i = 0; i < 14; ++i) y[i] = K0[zof(i)];
-#endif
+                for (int i = 0; i < 14; ++i) y[i] = K0[zof(i)];
+            }
             // end-of-step values go global -> stash without passing through registers (needed when the step ends)
 #pragma unroll
             for (int i = 0; i < 8; ++i) cp_async<sizeof(T)>(sh + (S_I + i) * 32, a.integ + i * N + e);
