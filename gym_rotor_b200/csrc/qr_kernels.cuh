@@ -21,16 +21,6 @@ __host__ __device__ constexpr int obs_stride_of(int O) { return (O + 3) & ~3; }
 #ifndef QR_RESET_BATCH
 #define QR_RESET_BATCH 24
 #endif
-// Warps of a block run the loop in LOCK STEP, in groups of QR_LOCKSTEP warps (0 = free running): the loop body is ~59 KB of
-// straight-line code, far beyond the 32 KB instruction cache of an SM, so every warp streams it from L2 on its own
-// (stall_no_instruction was the largest stall, 1.5 cycles per issued instruction); warps that pass the same code together
-// share the fetches.  Negative: groups by SM sub-partition (warp & 3).
-#ifndef QR_LOCKSTEP
-#define QR_LOCKSTEP 0          // single-step launches
-#endif
-#ifndef QR_LOCKSTEP_MULTI
-#define QR_LOCKSTEP_MULTI 0    // multi-step launches (long-running: the warps of a block drift fully out of phase)
-#endif
 #define QR_NSTATS 20   // QR_NUM_STATS of include/quadrotor_b200.h
 // 1: the next env's state is fetched global -> shared (cp.async into the park area of the stage storage, free until the reset
 // section) instead of into dead registers, so that no scoreboard of the end-of-step code is shared with loads on their way to
@@ -127,18 +117,6 @@ template <int BYTES> QR_DEV void cp_async(void* smem, const void* gmem) { memcpy
 QR_DEV void cp_async_wait_all() {}
 QR_DEV void cp_async_commit() {}
 template <int N> QR_DEV void cp_async_wait_group() {}
-#endif
-// Named barrier + AND-reduction over `threads` threads (a group of warps of the block); single-warp emulator: the own flag
-#if QR_PTX
-QR_DEV bool group_sync_and(int id, int threads, bool flag)
-{
-    unsigned r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.cta.red.and.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(r) : "r"(id), "r"(threads), "r"((unsigned)flag) : "memory");
-    return r != 0;
-}
-#else
-QR_DEV bool group_sync_and(int, int, bool flag) { return flag; }
 #endif
 template <typename T> QR_DEV int32_t& stash_i32(T* sh, int slot) { return *reinterpret_cast<int32_t*>(sh + slot * 32); }
 
@@ -266,21 +244,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     const EnvConst<T>& c = a.c;
     const int64_t N = a.n;
     const int NS = MULTI ? a.n_steps : 1;   // single-step kernels: the sub-step counter k folds to the constant 0
-    constexpr int LOCKSTEP = MULTI ? QR_LOCKSTEP_MULTI : QR_LOCKSTEP;
     constexpr bool PREFETCH_KS = QR_PREFETCH_KS != 0 && sizeof(T) == 4;   // float64: the loads into dead registers measured 4 % faster
-    int grp_id = 0, grp_threads = 0;   // lock-step group of this warp: named barrier (1 + group), threads in it
-    if (LOCKSTEP != 0) {
-        const int nw = (int)(blockDim.x >> 5);
-        if (LOCKSTEP > 0) {
-            constexpr int G_ = LOCKSTEP > 0 ? LOCKSTEP : 1;
-            grp_id = warp / G_;
-            grp_threads = 32 * min(G_, nw - grp_id * G_);
-        } else {
-            grp_id = warp & 3;
-            grp_threads = 32 * ((nw - grp_id + 3) >> 2);
-        }
-    }
-    bool all_drained = false;
     unsigned char* wbase = smem_raw + warp * warp_smem<T>::bytes;
     T* ks = reinterpret_cast<T*>(wbase);
     T* const sh = reinterpret_cast<T*>(wbase + warp_smem<T>::ks_bytes) + lane;   // stash slot j of this lane: sh[j * 32]
@@ -755,13 +719,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 __syncwarp();
             }
         }
-        if (LOCKSTEP == 0) {
-            if (drained && rq_n == 0 && cq_n == 0) break;
-        } else {
-            // a warp without work keeps pace (idle rounds) until its whole group is done: the barrier counts every warp
-            all_drained = group_sync_and(1 + grp_id, grp_threads, drained && rq_n == 0 && cq_n == 0);
-            if (all_drained) break;
-        }
+        if (drained && rq_n == 0 && cq_n == 0) break;
         // ---- A3: start the next env.step: goal, action, SO(3) check, f0 and the initial step size ----
         if (busy && need_init) {
             need_init = false;
