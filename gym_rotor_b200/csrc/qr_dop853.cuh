@@ -297,6 +297,19 @@ template <typename T> QR_DEV void rhs_z(const T* z, T W3, const Dyn<T>& d, T* k)
     k[13] = N::fma(d.kw1 * W1, W3, d.Mi1);
 }
 
+// out[0..8] = (M hat(W)) for the 3x3 matrix M held in positions 0..8 of a z vector (the first nine lines of rhs_z).
+template <typename T> QR_DEV void rhat_z(const T* m, T W1, T W2, T W3, T* out)
+{
+    using N = num<T>;
+    T t0, t1;
+    pmul<T>(-W2, m[4], m[5], t0, t1); pfma<T>(W3, m[2], m[3], t0, t1, out[0], out[1]);
+    pmul<T>(-W3, m[0], m[1], t0, t1); pfma<T>(W1, m[4], m[5], t0, t1, out[2], out[3]);
+    pmul<T>(-W1, m[2], m[3], t0, t1); pfma<T>(W2, m[0], m[1], t0, t1, out[4], out[5]);
+    out[6] = N::fma(m[7], W3, -(m[8] * W2));
+    out[7] = N::fma(m[8], W1, -(m[6] * W3));
+    out[8] = N::fma(m[6], W2, -(m[7] * W1));
+}
+
 // The acceptance test of ensure_SO3 (see so3_ok in qr_math.cuh) on the R part of a z vector.  Same tolerances; the
 // column products are packed, every comparison is ordered (a NaN fails), one predicate at the end.
 template <typename T> QR_DEV bool so3_ok_z(const T* z, T* mx = nullptr)
@@ -393,7 +406,7 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
     T z1[14], k1[14];
     v_fma_out<T>(h0, K0, z, z1);
     T W31 = N::fma(h0, d.w3dot, W3);
-    {
+    if (sizeof(T) == 8) {
         T R[9];
         z_get_R<T>(z1, R);
         const int fl = ensure_so3<T, true>(R);   // state_decomposition inside EoM; the probe leaves SO(3) in ~12 % of the steps
@@ -402,6 +415,29 @@ QR_DEV void dop853_begin(const T* x, const T* y, T W3, const Dyn<T>& d, const T 
 #pragma unroll
         for (int i = 0; i < 14; ++i) zr[i] = z1[i];
         z_set_R<T>(R, zr);
+        rhs_z<T>(zr, W31, d, k1);
+    } else {
+        // float32 mode: the probe's attitude is R (I + h0 hat(W)) with R on SO(3) (checked by the caller), so ensure_SO3's
+        // verdict and its result are known in closed form -- no test of nine products, no iteration, no divergence:
+        //   R1^T R1 - I = h0^2 (|W|^2 I - W W^T), det R1 = 1 + a2, a2 = h0^2 |W|^2: the determinant test (a2 <= 1e-5 + 1e-8)
+        //   is the binding one of the seven;
+        //   the projection U V^T (psvd) of R1 is R Rot(W / |W|, atan(h0 |W|)) = R + s R hat(W) + c R hat(W)^2 with
+        //   s = h0 / sqrt(1 + a2), c = (1 - cos) / |W|^2 = h0^2 rs^2 / (1 + rs), rs = 1 / sqrt(1 + a2)   (Rodrigues)
+        // and R hat(W) is the attitude part of f0.  Lanes whose probe passes use s = h0, c = 0: the Euler probe itself.
+        const T W1 = z[12], W2 = z[13];
+        const T n2 = N::fma(W3, W3, N::fma(W2, W2, W1 * W1));
+        const T hh = h0 * h0, a2 = hh * n2;
+        const bool pass = a2 <= (T)1.001e-5;
+        const T rs = N::rsqrt((T)1 + a2);
+        const T s = pass ? h0 : h0 * rs;
+        const T cc = pass ? (T)0 : hh * rs * rs * N::recip((T)1 + rs);
+        o.nproj += pass ? 0 : 1;
+        T m2[9], zr[14];
+        rhat_z<T>(K0, W1, W2, W3, m2);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) zr[i] = N::fma(cc, m2[i], N::fma(s, K0[i], z[i]));
+#pragma unroll
+        for (int i = 9; i < 14; ++i) zr[i] = z1[i];
         rhs_z<T>(zr, W31, d, k1);
     }
     T s2a = 0, s2b = 0;
@@ -605,6 +641,7 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
         v_mul<T>((T)dop_a(1, 0), K0, P);
         stage_finish<1, T>(z, P, d, c, F);
     }
+    // (float64 un-paired stages measured slower, 0.76 vs 0.91 G: profiles/r02/r02s_ab.txt)
     stage_pair<2, false, T>(z, K0, d, c, F, kl, kl_sa, lane, sb, s5);
     stage_pair<4, false, T>(z, K0, d, c, F, kl, kl_sa, lane, sb, s5);
     stage_pair<6, false, T>(z, K0, d, c, F, kl, kl_sa, lane, sb, s5);
