@@ -683,9 +683,13 @@ QR_DEV bool dop853_attempt(T* x, T* y, T& W3, const Dyn<T>& d, const T Tend, con
 // instruction-cache space; its stage derivatives live in local memory.  Same arguments as dop853_attempt, passed
 // through memory (the caller copies its registers in and out).
 template <typename T>
-__device__ __noinline__ bool dop853_attempt_checked(T* x, T* y, T* W3p, const Dyn<T>* dp, const T Tend, const T rtol, const T atol, T* K0, OdeLane<T>* op)
+__device__ __noinline__ bool dop853_attempt_checked(T* x, T* zio, T* W3p, const Dyn<T>* dp, const T Tend, const T rtol, const T atol, T* K0, OdeLane<T>* op)
 {
+    // zio: the 14 integrated components in the INTERNAL order, in and out (the caller's copies travel through local memory as
+    // 8/16-byte vectors: in the internal order those are the register pairs the hot loop works on, see ensure_so3)
     using N = num<T>;
+    T y[14];
+    from_z<T>(zio, y);
     const Dyn<T> d = *dp;
     OdeLane<T>& o = *op;
     const T min_step = (T)10 * N::ulp_up(o.t);
@@ -751,6 +755,7 @@ __device__ __noinline__ bool dop853_attempt_checked(T* x, T* y, T* W3p, const Dy
     T W3v = W3;
     const bool fin = dop853_conclude<T>(x, y, W3v, d, Tend, rtol, atol, K0, o, h, t_new, too_small, z, sb, s5, s3, xnew, x5, x3, nproj, bad);
     *W3p = W3v;
+    to_z<T>(y, zio);
     return fin;
 }
 

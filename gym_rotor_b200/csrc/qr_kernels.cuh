@@ -892,18 +892,18 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             // registers never have their address taken.
             if (__any_sync(FULL, live && ode.checked != 0)) {
                 if (live && ode.checked != 0) {
-                    T tx[3], ty[14], tK[14], tW3 = W3;
+                    T tx[3], ty[14], tK[14], tW3 = W3;   // ty: internal order (see dop853_attempt_checked)
                     Dyn<T> td = d;
                     OdeLane<T> to = ode;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) tx[i] = x[i];
 #pragma unroll
-                    for (int i = 0; i < 14; ++i) { ty[i] = y[i]; tK[i] = K0[i]; }
+                    for (int i = 0; i < 14; ++i) { ty[zof(i)] = y[i]; tK[i] = K0[i]; }
                     fin = dop853_attempt_checked<T>(tx, ty, &tW3, &td, c.dt, c.rtol, c.atol, tK, &to);
 #pragma unroll
                     for (int i = 0; i < 3; ++i) x[i] = tx[i];
 #pragma unroll
-                    for (int i = 0; i < 14; ++i) { y[i] = ty[i]; K0[i] = tK[i]; }
+                    for (int i = 0; i < 14; ++i) { y[i] = ty[zof(i)]; K0[i] = tK[i]; }
                     W3 = tW3; ode = to;
                 }
             }

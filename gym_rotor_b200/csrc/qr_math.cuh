@@ -138,12 +138,14 @@ template <typename T> QR_DEV bool so3_ok(const T* R, T* defect = nullptr)
 // psvd + "U @ VT.T" (quad_utils.py:138-140, 226-240): R <- U diag(1,1,det U det Vt) Vt by one-sided
 // Jacobi.  Rare path (only the Euler probe of the initial-step selection leaves SO(3) by > 1e-5), kept
 // out of line so that it does not add register pressure to the integrator.  Returns 1 on failure.
-template <typename T> __device__ __noinline__ int project_so3(T* R)
+// ZORDER: the caller hands the matrix over in the integrator's internal component order (qr_so3_zpos), see ensure_so3.
+QR_DEV constexpr int qr_so3_zpos(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 6 : i == 3 ? 2 : i == 4 ? 3 : i == 5 ? 7 : i == 6 ? 4 : i == 7 ? 5 : 8; }
+template <typename T, bool ZORDER = false> __device__ __noinline__ int project_so3(T* R)
 {
     using N = num<T>;
     T A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int i = 0; i < 9; ++i) {
-        A[i] = R[i];
+        A[i] = R[ZORDER ? qr_so3_zpos(i) : i];
         if (!(N::abs(A[i]) <= N::huge)) return 1;
     }
     for (int sweep = 0; sweep < 30; ++sweep) {
@@ -198,7 +200,7 @@ template <typename T> __device__ __noinline__ int project_so3(T* R)
                 if (k == jmin) u *= sgn;
                 s += u * V[j + 3 * k];
             }
-            R[i + 3 * j] = s;
+            R[ZORDER ? qr_so3_zpos(i + 3 * j) : i + 3 * j] = s;
         }
     return bad;
 }
@@ -254,12 +256,17 @@ template <typename T, bool NEWTON = false> QR_DEV int ensure_so3(T* R)
     T defect;
     if (so3_ok(R, &defect)) return 0;
     if (NEWTON) { if (defect < (T)0.05 && polar_newton<T>(R, defect)) return 1; }
+    // (rare path) the matrix travels to the out-of-line routine through local memory as 16-byte vectors, i.e. in groups of
+    // four consecutive registers.  It is handed over in the integrator's internal order (qr_dop853.cuh: b1.xy b2.xy | b3.xy
+    // b1.z b2.z | b3.z), so that those groups are unions of the register PAIRS the packed instructions work on: in
+    // column-major order ptxas laid the caller's persistent attitude out for these stores and assembled three of the seven
+    // pairs with two moves at each of their uses in the hot loop
     T tmp[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) tmp[i] = R[i];
-    int bad = project_so3<T>(tmp);
+    for (int i = 0; i < 9; ++i) tmp[qr_so3_zpos(i)] = R[i];
+    int bad = project_so3<T, true>(tmp);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = own_reg(tmp[i]);   // (rare path) no vector reload straight into the caller's registers
+    for (int i = 0; i < 9; ++i) R[i] = own_reg(tmp[qr_so3_zpos(i)]);
     return 1 | (bad << 1);
 }
 

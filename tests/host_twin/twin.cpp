@@ -100,7 +100,12 @@ int step_one(const qr_config* cfg, const double* state, const double* integ, con
     int guard = 0;
     while (!fin && guard++ < 100000) {
         fin = dop853_attempt<T>(x, y, W3, d, c.dt, c.rtol, c.atol, K0, ode, ks, 0, true);
-        if (ode.checked) fin = dop853_attempt_checked<T>(x, y, &W3, &d, c.dt, c.rtol, c.atol, K0, &ode);   // as phase B of k_step
+        if (ode.checked) {   // as phase B of k_step: the redo takes and returns the components in the internal order
+            T tz[14];
+            to_z<T>(y, tz);
+            fin = dop853_attempt_checked<T>(x, tz, &W3, &d, c.dt, c.rtol, c.atol, K0, &ode);
+            from_z<T>(tz, y);
+        }
     }
     // ---- A1
     for (int i = 0; i < 3; ++i) r.x[i] = x[i];
