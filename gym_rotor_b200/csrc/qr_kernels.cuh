@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 
     for (;;) {
         // =============================== phase A ===============================
+        if (PREFETCH_KS) __syncwarp();   // the stage storage is written again below (A0's fetch-ahead lands in its park area): phase B must be over for every lane
         const unsigned finmask = __ballot_sync(FULL, fin);
         // ---- A0: lanes that are idle, or about to release their env, are given the next env of the warp's sequence
         // NOW and start fetching it with cp.async (no register in between): the state into the park area of the stage
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     // K0 and d are dead for a lane that is idle or has finished its step (A1 only reads ode's counters)
                     // (K0 is kept in the integrator's internal order, qr_dop853.cuh: the fetched state lands in the
                     //  matching positions, so that y and K0 agree on which components form a register pair)
-                    if (PREFETCH_KS) {
+                    if (PREFETCH_KS) {   // (phase B of every lane is over: the __syncwarp at the top of the round)
 #pragma unroll
                         for (int i = 0; i < 18; ++i) cp_async<sizeof(T)>(ks + 1024 + i * 32 + lane, a.state + i * N + ee);
                     } else {
