@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     // cheap envs simply take more tiles, so the persistent grid drains evenly
     const int64_t n_range = a.env_hi - a.env_lo;
     const int64_t ntiles = (n_range + 31) >> 5;
+    // (dealing the tiles round robin instead -- no atomic, whose answer is the most stalled-on instruction of single-step
+    //  launches -- measured 1.5 % to 3.7 % slower: profiles/r02/r02aa_ab_static_tiles.txt)
     int64_t tile_base = 0;    // warp-uniform: first env of the tile currently being handed out
     int tile_pos = 32;        // warp-uniform: envs of that tile already taken (32 = none left)
     bool exhausted = false;   // warp-uniform: the counter ran past the last tile
