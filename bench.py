@@ -14,8 +14,9 @@ registers) followed by the sum all-reduce of the episode statistics (NCCL) -- so
 path's one collective, resets occur at their true rate, and 20 steps are 2560 env-steps per env.
 
 Also in the line: `k1` (one env.step() per launch, actions read from HBM, all per-step outputs written -- the figure
-of round 1), `e2e` (qr_step_host with pinned host buffers) with a bare-copy ceiling, `configs` (BASELINE.json configs
-3 and 5, float64 mode, trajectory tracking; N=1 only), the CPU legs (reference cost structure on all host cores).
+of round 1), `tracking` (the same rollout with figure-eight goals generated in the kernel), `e2e` (qr_step_host with
+pinned host buffers) with a bare-copy ceiling -- all three at every N --, `configs` (BASELINE.json configs 3 and 5,
+float64 mode; N=1 only), the CPU legs (reference cost structure on all host cores).
 """
 import argparse
 import json
@@ -279,21 +280,6 @@ def sub_configs(torch, vec_env, dev, seed, quick):
                             "fp64_issue_frac": ALG_FLOPS * n / (ms * 1e-3) / (torch.cuda.get_device_properties(dev).multi_processor_count * 64 * 2 * _peaks()[1] * 1e6)}
     env.close()
     del pool
-    # trajectory tracking: on-device figure-eight goals (trajectory_generator mode 6), evaluated inside the step kernel
-    n = 1 << 21
-    env = _make_env(vec_env, n, "MONO", torch.float32, dev, seed, "eight", False, 0)
-    try:
-        ms = _timed(torch, dev, lambda i: env.rollout(128), steps(6), 2)
-        st = env.stats()
-        out["tracking_eight_f32_2^21"] = {"value": n * 128 / (ms * 1e-3), "unit": "env-steps/s", "ms_per_launch": ms,
-                                          "workload": "CoupledWrapper, 2^21 envs, figure-eight goals generated in the step kernel before every step, "
-                                                      "128 env.step per launch, Philox actions, auto reset", "mean_dop853_attempts": _attempts(st)}
-    except Exception as ex:   # a library without the in-kernel trajectory modes
-        pool = [torch.rand((n, 4), device=dev, dtype=torch.float32) * 2 - 1 for _ in range(8)]
-        ms = _timed(torch, dev, lambda i: env.step(pool[i % 8]), steps(100), steps(10))
-        out["tracking_eight_f32_2^21"] = {"value": n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
-                                          "workload": "CoupledWrapper, 2^21 envs, figure-eight goals: goal-update kernel + step kernel per env.step (%s)" % ex}
-    env.close()
     return out
 
 
@@ -421,6 +407,34 @@ def run_ours(args):
               "fp_issue_frac": None}
         del kpool
 
+    # ---- trajectory tracking (north_star: "random-action and trajectory-tracking workloads at 1, 2, 4 and 8 GPUs"): the same
+    # rollout with figure-eight goals generated in the step kernel before every step (trajectory_generator mode 6)
+    tracking = None
+    if fused > 1 and not args.policy and not args.no_extra and fw != "QUAD" and args.goal == "traj0":
+        env_t = _make_env(vec_env, n, fw, dtype, dev, args.seed, "eight", False, rank * n)
+        for i in range(2):
+            env_t.rollout(fused)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t_steps = 4
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for i in range(t_steps):
+            env_t.rollout(fused)
+        b1.record()
+        torch.cuda.synchronize(dev)
+        tt = torch.tensor([b0.elapsed_time(b1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        st_t = allreduce_stats(env_t, dev) if world > 1 else env_t.stats()
+        t_ms = float(tt.item()) / t_steps
+        tracking = {"value": float(n) * world * fused / (t_ms * 1e-3), "unit": "env-steps/s", "ms_per_launch": t_ms, "launches": t_steps,
+                    "workload": "same rollout (%d env.step per launch, Philox actions, auto reset) with figure-eight goals generated in the step "
+                                "kernel before every step (trajectory_generator mode 6, main.py:145-147)" % fused,
+                    "mean_dop853_attempts": _attempts(st_t), "mean_episode_length": float(st_t[3] / max(1.0, st_t[0]))}
+        env_t.close()
+
     # ---- end to end through the host-buffer entry point (qr_step_host): pinned host actions in, obs/reward/done out
     e2e_steps = max(3, min(args.steps, 20))
     act_h = [torch.empty((n, A), dtype=torch.float32).uniform_(-1, 1).pin_memory() for _ in range(2)]
@@ -541,6 +555,9 @@ def run_ours(args):
                              "note": "not the binding bound: the K=1 launch (key k1) moves %d B per env-step" % bytes_per},
             "device": {"name": props.name, "sms": sms, "sm_max_mhz": sm_max, "total_memory_gb": props.total_memory / 2 ** 30},
         }
+        if tracking is not None:
+            tracking["fraction_of_headline"] = tracking["value"] / value
+            line["tracking"] = tracking
         if k1 is not None:
             k1["fp_issue_frac"] = ALG_FLOPS * (k1["value"] / world) / 1e12 / fp_peak
             k1["hbm_frac"] = k1["hbm_gbs"] / hbm_peak

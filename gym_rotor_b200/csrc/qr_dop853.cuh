@@ -196,6 +196,35 @@ template <typename T> QR_DEV void ks_store(T* kl, unsigned kl_sa, int lane, int 
 #pragma unroll
     for (int g = 0; g < 7; ++g) *reinterpret_cast<double2*>(p + g * 64) = make_double2((double)k[2 * g], (double)k[2 * g + 1]);
 }
+// float64 on the device: the same accesses as explicit (volatile) ld/st.shared -- as plain C++ loads the compiler hoists
+// them far ahead of their use, and at 255 registers every hoisted stage derivative is spilled (the float64 kernel spent
+// most of its time waiting for local memory: 278 local loads per 32 env-steps, long_scoreboard 3.3 per issued instruction)
+#if QR_PTX
+template <> QR_DEV void ks_load<double>(const double* kl, unsigned kl_sa, int lane, int slot, double* k)
+{
+    (void)kl;
+    const unsigned sa = kl_sa + (unsigned)(slot * QR_SLOT_ELEMS * 8) - (unsigned)lane * 16u;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(k[0]), "=d"(k[1]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+512];" : "=d"(k[2]), "=d"(k[3]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+1024];" : "=d"(k[4]), "=d"(k[5]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+1536];" : "=d"(k[6]), "=d"(k[7]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+2048];" : "=d"(k[8]), "=d"(k[9]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+2560];" : "=d"(k[10]), "=d"(k[11]) : "r"(sa) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+3072];" : "=d"(k[12]), "=d"(k[13]) : "r"(sa) : "memory");
+}
+template <> QR_DEV void ks_store<double>(double* kl, unsigned kl_sa, int lane, int slot, const double* k)
+{
+    (void)kl;
+    const unsigned sa = kl_sa + (unsigned)(slot * QR_SLOT_ELEMS * 8) - (unsigned)lane * 16u;
+    asm volatile("st.shared.v2.f64 [%2], {%0,%1};" :: "d"(k[0]), "d"(k[1]), "r"(sa) : "memory");
+    asm volatile("st.shared.v2.f64 [%2+512], {%0,%1};" :: "d"(k[2]), "d"(k[3]), "r"(sa) : "memory");
+    asm volatile("st.shared.v2.f64 [%2+1024], {%0,%1};" :: "d"(k[4]), "d"(k[5]), "r"(sa) : "memory");
+    asm volatile("st.shared.v2.f64 [%2+1536], {%0,%1};" :: "d"(k[6]), "d"(k[7]), "r"(sa) : "memory");
+    asm volatile("st.shared.v2.f64 [%2+2048], {%0,%1};" :: "d"(k[8]), "d"(k[9]), "r"(sa) : "memory");
+    asm volatile("st.shared.v2.f64 [%2+2560], {%0,%1};" :: "d"(k[10]), "d"(k[11]), "r"(sa) : "memory");
+    asm volatile("st.shared.v2.f64 [%2+3072], {%0,%1};" :: "d"(k[12]), "d"(k[13]), "r"(sa) : "memory");
+}
+#endif
 // float32: explicit ld/st.shared on the 32-bit shared-window address with immediate slot offsets (no 64-bit pointer math)
 template <> QR_DEV void ks_load<float>(const float* kl, unsigned kl_sa, int lane, int slot, float* k)
 {
