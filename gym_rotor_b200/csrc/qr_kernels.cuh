@@ -410,6 +410,11 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (GOAL1) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) { r.goal[i] = 0; r.goal[3 + i] = 0; r.goal[6 + i] = sh[(S_B1D + i) * 32]; r.goal[9 + i] = sh[(S_WD + i) * 32]; }
+                } else if (MODE != 0 && c.goal_mode >= 2) {   // trajectory goal of this step: left in the stash by A3 (kernel-uniform)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { r.goal[i] = sh[(S_B1D + i) * 32]; r.goal[3 + i] = sh[(S_WD + i) * 32]; }
+                    r.goal[6] = sh[(S_NB1D + 0) * 32]; r.goal[7] = sh[(S_NB1D + 1) * 32]; r.goal[8] = 0;
+                    r.goal[9] = 0; r.goal[10] = 0; r.goal[11] = sh[(S_NB1D + 2) * 32];
                 } else {
 #pragma unroll
                     for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * N + e];
@@ -814,20 +819,39 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             r.m = p_m; r.d = p_d; r.J1 = p_J1; r.J3 = p_J3; r.c_tf = p_ctf; r.c_tw = p_ctw;
             if (!GOAL1 && MODE != 0 && c.goal_mode >= 2) {
                 // trajectory_generator.get_desired(state, mode) + set_goal_state on the pre-step state, as the trainer calls
-                // them before every env.step (main.py:145-147): hover / circle / eight / take-off / land / stay.  Per-env
-                // trajectory state and goal go through their HBM arrays (the observation at the end of the step reads the
-                // goal from there, like an external one); kernel-uniform branch.
+                // them before every env.step (main.py:145-147): hover / circle / eight / take-off / land / stay (kernel-uniform
+                // branch).  The goal of the step (xd, vd, b1d.xy, Wd.z: the other three are zero in every mode) and what
+                // changes per call of the trajectory state (clock, flags, b1d_dot) live in nine + four stash slots that this
+                // configuration does not use otherwise; an env that keeps its lane reads only the trajectory's constants from
+                // HBM and writes nothing back before its last sub-step.
                 T ts[12], gl[12];
+                const bool from_hbm = !MULTI || staged;
+                if (from_hbm) {
 #pragma unroll
-                for (int i = 0; i < 12; ++i) { ts[i] = a.traj[i * N + e]; gl[i] = a.goal[i * N + e]; }
+                    for (int i = 0; i < 12; ++i) { ts[i] = a.traj[i * N + e]; gl[i] = a.goal[i * N + e]; }
+                } else {
+#pragma unroll
+                    for (int i = 2; i < 9; ++i) ts[i] = a.traj[i * N + e];
+                    ts[0] = sh[(S_ACT + 0) * 32]; ts[1] = sh[(S_ACT + 1) * 32]; ts[9] = sh[(S_ACT + 2) * 32]; ts[10] = sh[(S_ACT + 3) * 32];
+                    ts[11] = 0;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { gl[i] = sh[(S_B1D + i) * 32]; gl[3 + i] = sh[(S_WD + i) * 32]; }
+                    gl[6] = sh[(S_NB1D + 0) * 32]; gl[7] = sh[(S_NB1D + 1) * 32]; gl[8] = 0;
+                    gl[9] = 0; gl[10] = 0; gl[11] = sh[(S_NB1D + 2) * 32];
+                }
                 const T Wv[3] = {y[12], y[13], W3};
                 const int fl0 = (int)ts[1];
                 traj_desired<T>(traj_ref_mode<>(c.goal_mode), x, y, y + 3, Wv, ts, gl, (T)0, (T)0, c.dt);
 #pragma unroll
-                for (int i = 0; i < 12; ++i) a.goal[i * N + e] = gl[i];
-                // per call only the clock, the flags and b1d_dot change; the rest is set when a trajectory (or the manual
-                // mode after it) starts
-                a.traj[0 * N + e] = ts[0]; a.traj[1 * N + e] = ts[1]; a.traj[9 * N + e] = ts[9]; a.traj[10 * N + e] = ts[10];
+                for (int i = 0; i < 3; ++i) { sh[(S_B1D + i) * 32] = gl[i]; sh[(S_WD + i) * 32] = gl[3 + i]; }
+                sh[(S_NB1D + 0) * 32] = gl[6]; sh[(S_NB1D + 1) * 32] = gl[7]; sh[(S_NB1D + 2) * 32] = gl[11];
+                if (MULTI) { sh[(S_ACT + 0) * 32] = ts[0]; sh[(S_ACT + 1) * 32] = ts[1]; sh[(S_ACT + 2) * 32] = ts[9]; sh[(S_ACT + 3) * 32] = ts[10]; }
+                if (k == NS - 1) {   // the env leaves the lane after this step: goal and trajectory state back to their arrays
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) a.goal[i * N + e] = gl[i];
+                    a.traj[0 * N + e] = ts[0]; a.traj[1 * N + e] = ts[1]; a.traj[9 * N + e] = ts[9]; a.traj[10 * N + e] = ts[10];
+                }
+                // the rest of the trajectory state is set when a trajectory (or the manual mode after it) starts
                 if (((int)ts[1] ^ fl0) & 5) {
 #pragma unroll
                     for (int i = 2; i < 9; ++i) a.traj[i * N + e] = ts[i];
