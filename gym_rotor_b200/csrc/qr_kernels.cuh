@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     bool has_next = false;   // K0 / d hold the NEXT env's state (loads in flight), the stash its action etc.
     bool fresh = false;      // the env was adopted in this round's A2: its action / parameters / b1d are in the stash
     bool r_ok = false;       // multi-step launches: the attitude passed ensure_SO3 in the observation that ended the previous sub-step
+    bool obs_in_tile = false;   // policy rollouts: this round's A1 left the lane's observation row in the shared tile (stage storage)
     int64_t e_next = 0;
     int k_next = 0;          // multi-step launches: the sub-step at which the fetched env goes on (a reset env resumes mid-rollout)
 #pragma unroll
@@ -444,12 +445,16 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     obs1 = a.obs_roll + ((int64_t)k * N + e) * O;
                     if (last || POLICY) obs2 = a.obs + e * OS;   // POLICY: the actor reads a.obs at the next sub-step
                 } else if (last || POLICY) obs1 = a.obs + e * OS;
-                if (coop) {
+                if (coop || (POLICY && MULTI)) {
+                    // (policy rollouts: the actor of the next sub-step reads the row from here, not from HBM -- unless a reset
+                    //  batch reuses the stage storage in between, see A3)
                     float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
 #pragma unroll
                     for (int i = 0; i < OS / 4; ++i)
                         reinterpret_cast<float4*>(tile + lane * OS)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], (4 * i + 3 < O) ? o[4 * i + 3] : 0.f);
-                } else {
+                    if (POLICY && MULTI) obs_in_tile = true;
+                }
+                if (!coop) {
                     {   // rows inside a.obs are 16-byte aligned and padded: vector stores; caller's rollout storage: scalar
                         float op[OS];
 #pragma unroll
@@ -666,6 +671,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 rq_n -= n_now;
             }
             if (__any_sync(FULL, do_reset)) {
+                obs_in_tile = false;   // the reset scratch and the park area overwrite the tile
                 __syncwarp();
                 T* const pk = ks + 1024 + lane;   // park slot j of this lane: pk[j * 32] (the reset scratch is ks[0 .. 1023])
 #define QR_PKI(j) (*reinterpret_cast<int32_t*>(pk + (j) * 32))
@@ -784,9 +790,16 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             if (POLICY) {
                 // obs -> action with the compiled actor(s); the row was written by this env's previous step (by this
                 // thread, or by its warp through the shared tile / by an earlier launch)
-                float xo[23], af[5];
+                float xo[24], af[5];
+                if (MULTI && !staged && obs_in_tile) {
+                    const float4* row = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ks) + lane * OS);
 #pragma unroll
-                for (int i = 0; i < O; ++i) xo[i] = a.obs[e * OS + i];
+                    for (int i = 0; i < OS / 4; ++i) { const float4 v = row[i]; xo[4 * i] = v.x; xo[4 * i + 1] = v.y; xo[4 * i + 2] = v.z; xo[4 * i + 3] = v.w; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < O; ++i) xo[i] = a.obs[e * OS + i];
+                }
+                obs_in_tile = false;
                 if (MODE == 1) actor_td3_mono(xo, af);
                 else { actor_td3_modul1(xo, af); actor_td3_modul2(xo + 15, af + 4); }
 #pragma unroll

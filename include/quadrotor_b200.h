@@ -151,7 +151,10 @@ int qr_policy_td3(qr_handle* h, float* actions, void* stream);
  * (as qr_policy_td3) evaluated in the kernel on the env's latest observation -- the evaluation loop of
  * main.py:304-365 (obs -> agent.choose_action -> env.step) in one launch; the observation buffer must hold the
  * current observations (qr_norm_error_state after a reset).  obs_out/reward_out/done_out: device
- * [n_steps][N][..] or NULL to keep only the last step's outputs in the qr_buffers views. */
+ * [n_steps][N][..] or NULL to keep only the last step's outputs in the qr_buffers views.  1 <= n_steps <= 32767.
+ * With autoreset, an env whose episode ends inside the launch is reset there (batched per warp) and goes on stepping:
+ * its row of obs_out at that sub-step holds the first observation of the new episode, like qr_step's obs.
+ * All on-device goal modes are evaluated inside the launch before every sub-step. */
 int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, float* obs_out, void* reward_out,
                uint8_t* done_out, void* stream);
 

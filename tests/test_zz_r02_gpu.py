@@ -23,22 +23,22 @@ def _start(e, env_type="train"):
     e.stats()
 
 
-@pytest.mark.parametrize("goal", ["hover", "circle", "eight"])
-def test_trajectory_goal_inside_the_step_kernel_rollout_equals_single_steps(goal):
+@pytest.mark.parametrize("fw,goal", [("MONO", "hover"), ("MONO", "circle"), ("MONO", "eight"), ("MODUL", "eight")])
+def test_trajectory_goal_inside_the_step_kernel_rollout_equals_single_steps(fw, goal):
     """Tracking workloads: the goal of every step is generated in the step kernel (get_desired before env.step,
     main.py:145-147).  One 24-step launch == 24 single-step launches == goal-update kernel + external-goal step, with auto
     reset restarting the trajectories (float64: bit-identical)."""
     n, K = 4096, 24
     kw = dict(seed=8, autoreset=True, goal_mode=goal, max_episode_steps=10)
-    ea, eb = _env(n, "MONO", torch.float64, **kw), _env(n, "MONO", torch.float64, **kw)
+    ea, eb = _env(n, fw, torch.float64, **kw), _env(n, fw, torch.float64, **kw)
     for e in (ea, eb):
         _start(e)
     g = torch.Generator(device="cuda:0"); g.manual_seed(4)
-    acts = (torch.rand((K, n, 4), device="cuda:0", generator=g, dtype=torch.float64) * 2 - 1) * 0.4
+    acts = (torch.rand((K, n, ea.act_dim), device="cuda:0", generator=g, dtype=torch.float64) * 2 - 1) * 0.4
     obs_r, rew_r, done_r = ea.rollout(K, actions=acts, store=True)
     for k in range(K):
         obs, rew, done, _, _ = eb.step(acts[k])
-        assert torch.equal(obs[0], obs_r[k]) and torch.equal(rew, rew_r[k]) and torch.equal(done, done_r[k].bool()), k
+        assert torch.equal(torch.cat(obs, dim=1), obs_r[k]) and torch.equal(rew, rew_r[k]) and torch.equal(done, done_r[k].bool()), k
     for name in ("state_soa", "integ_soa", "goal_soa", "traj_soa", "params_soa", "ep_length"):
         assert torch.equal(getattr(ea, name), getattr(eb, name)), name
     sa, sb = ea.stats(), eb.stats()
