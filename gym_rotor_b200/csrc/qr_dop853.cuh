@@ -358,11 +358,18 @@ template <typename T> QR_DEV bool so3_ok_z(const T* z, T* mx = nullptr)
     const T e01 = N::fma(z[6], z[7], s0) + s1;
     const T e02 = N::fma(z[6], z[8], u0) + u1;
     const T e12 = N::fma(z[7], z[8], w0) + w1;
-    // det R - 1 = b1 . (b2 x b3) - 1
-    const T cx = N::fma(z[3], z[8], -(z[7] * z[5]));
-    const T cy = N::fma(z[7], z[4], -(z[2] * z[8]));
-    const T cz = N::fma(z[2], z[5], -(z[3] * z[4]));
-    const T dm1 = N::fma(z[0], cx, N::fma(z[1], cy, N::fma(z[6], cz, (T)-1)));
+    // det R - 1.  float64: b1 . (b2 x b3) - 1.  float32: det R = sqrt(det(I + E)) = 1 + tr(E) / 2 + O(|E|^2) with E = R^T R - I
+    // just computed; where the test can pass at all |E| <= 2e-5, so the neglected terms are below 1e-9 -- a hundred times
+    // less than the rounding error of the nine-product determinant in float32 (~2e-7), against a threshold of 1e-5
+    T dm1;
+    if (sizeof(T) == 4) {
+        dm1 = (T)0.5 * ((e00 + e11) + e22);
+    } else {
+        const T cx = N::fma(z[3], z[8], -(z[7] * z[5]));
+        const T cy = N::fma(z[7], z[4], -(z[2] * z[8]));
+        const T cz = N::fma(z[2], z[5], -(z[3] * z[4]));
+        dm1 = N::fma(z[0], cx, N::fma(z[1], cy, N::fma(z[6], cz, (T)-1)));
+    }
     if (mx && sizeof(T) == 8) {
         // float64 (no NaN-propagating 3-input maximum there): the seven comparisons per stage, folded into the first maximum
         const bool ok = (N::abs(e00) <= tol + tol) & (N::abs(e11) <= tol + tol) & (N::abs(e22) <= tol + tol) & (N::abs(e01) <= tol) &

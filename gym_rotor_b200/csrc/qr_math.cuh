@@ -128,7 +128,8 @@ template <typename T> QR_DEV bool so3_ok(const T* R, T* defect = nullptr)
     T d12 = N::fma(R[5], R[8], N::fma(R[4], R[7], R[3] * R[6]));
     T dg = N::max(N::max(N::abs(d00 - (T)1), N::abs(d11 - (T)1)), N::abs(d22 - (T)1));
     T od = N::max(N::max(N::abs(d01), N::abs(d02)), N::abs(d12));
-    T dt = N::abs(det3(R) - (T)1);
+    // float32: det R - 1 = tr(R^T R - I) / 2 + O(1e-9) wherever the test can pass (see so3_ok_z in qr_dop853.cuh)
+    T dt = (sizeof(T) == 4) ? N::abs((T)0.5 * (((d00 - (T)1) + (d11 - (T)1)) + (d22 - (T)1))) : N::abs(det3(R) - (T)1);
     // fmax drops NaNs, so test finiteness through a sum that propagates them
     T nanprobe = (d00 + d11 + d22) + (d01 + d02 + d12);
     if (defect) *defect = (nanprobe == nanprobe) ? N::max(dg, od) : (T)1;   // max |RtR - I| (1 if not finite)
