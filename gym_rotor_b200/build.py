@@ -16,7 +16,12 @@ OBJ_DIR = os.path.join(CSRC, "_build")
 DEPS = ["quadrotor_b200.cu", "qr_step_tu.cu", "qr_kernels.cuh", "qr_env.cuh", "qr_traj.cuh", "qr_dop853.cuh", "qr_math.cuh", "dop853_tableau.h",
         os.path.join("generated", "actor_td3.cuh"),
         os.path.join("..", "..", "include", "quadrotor_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+# -prec-div / -prec-sqrt = false concern SINGLE precision only: the float32 mode's remaining `/` and sqrtf (its bar is 1e-5 of
+# the reference) become MUFU + one Newton step without the slow-path call (+2 % at 128 steps per launch, -850 instructions of
+# code; profiles/r02/r02ah_ab_fast_div.txt).  The float64 (parity) mode divides and takes roots in double precision, and its
+# float32 observation / reward arithmetic uses explicit __f*_rn intrinsics, which these flags do not touch (GPU suite: 60 green).
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-prec-div=false", "-prec-sqrt=false",
+              "-Xcompiler", "-fPIC"]
 # (object name, source, defines): the C ABI + companion kernels, then the step kernel per (dtype, mode, policy)
 UNITS = [("abi", "quadrotor_b200.cu", [])] + [
     ("step_%s_m%d_p%d" % (t, m, p), "qr_step_tu.cu", ["QR_TU_T=%s" % t, "QR_TU_MODE=%d" % m, "QR_TU_POLICY=%d" % p])
