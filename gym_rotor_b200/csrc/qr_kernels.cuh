@@ -488,11 +488,14 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
                 if (MODE != 0) {
                     // benchmark_reward_func(ex, eb1) = interp(-|ex| - |eb1|, [-2, 0], [0, 1]) (utils/utils.py:21-47) on this
-                    // step's observation, and the trainer's "solved" relabel at the time limit (main.py:169-173)
+                    // step's observation (a per-step statistic: with diagnostics only), and the trainer's "solved" relabel at
+                    // the time limit (main.py:169-173)
                     const float ex0 = o[0] * (float)c.x_lim, ex1 = o[1] * (float)c.x_lim, ex2 = o[2] * (float)c.x_lim;
-                    const float eb1 = o[MODE == 1 ? 18 : 15] * 3.14159265358979f;
-                    const float rb = -sqrtf(fmaf(ex2, ex2, fmaf(ex1, ex1, ex0 * ex0))) - fabsf(eb1);
-                    brew = fminf(fmaxf(fmaf(rb, 0.5f, 1.0f), 0.f), 1.f);
+                    if (c.diagnostics) {
+                        const float eb1 = o[MODE == 1 ? 18 : 15] * 3.14159265358979f;
+                        const float rb = -sqrtf(fmaf(ex2, ex2, fmaf(ex1, ex1, ex0 * ex0))) - fabsf(eb1);
+                        brew = fminf(fmaxf(fmaf(rb, 0.5f, 1.0f), 0.f), 1.f);
+                    }
                     solved = trunc && fabsf(ex0) <= 0.03f && fabsf(ex1) <= 0.03f && fabsf(ex2) <= 0.03f && rew[0] != -1.0;
                 }
                 // per-step scalar outputs
@@ -557,22 +560,27 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 const int att = (nf - 2) / 12;
                 const int s_nfev = __reduce_add_sync(FULL, nf);
                 const int s_proj = __reduce_add_sync(FULL, nproj);
-                // attempt histogram: with diagnostics only (kernel-uniform); the mean is always available from the nfev sum (2 + 12 per attempt)
+                // per-step sums -- attempt histogram, reward, benchmark reward -- with diagnostics only (kernel-uniform); the mean
+                // attempt count is always available from the nfev sum (2 + 12 per attempt), returns from the episode statistics
                 unsigned m1 = 0, m2 = 0, m3 = 0, m4 = 0;
+                float s_rew = 0.f, s_brew = 0.f;
                 if (c.diagnostics) {
                     m1 = __ballot_sync(FULL, fin && att == 1); m2 = __ballot_sync(FULL, fin && att == 2);
                     m3 = __ballot_sync(FULL, fin && att == 3); m4 = __ballot_sync(FULL, fin && att >= 4);
+                    s_rew = warp_sum_f(rew0f);
+                    if (MODE != 0) s_brew = warp_sum_f(brew);
                 }
                 const unsigned mbad = __ballot_sync(FULL, fin && st != 0);
-                const float s_rew = warp_sum_f(rew0f);
-                const float s_brew = (MODE != 0) ? warp_sum_f(brew) : 0.f;
                 const unsigned msolved = (MODE != 0) ? __ballot_sync(FULL, solved) : 0u;
                 const unsigned mres = __ballot_sync(FULL, ep_done);
                 if (lane == 0) {
-                    if (MODE != 0) { ws[16] += (double)s_brew; if (msolved) ws[17] += (double)__popc(msolved); }
+                    if (MODE != 0 && msolved) ws[17] += (double)__popc(msolved);
                     ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev; ws[15] += (double)s_proj;
-                    if (c.diagnostics) { ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4); }
-                    ws[8] += (double)__popc(mbad); ws[14] += (double)s_rew;
+                    if (c.diagnostics) {
+                        ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
+                        ws[14] += (double)s_rew; ws[16] += (double)s_brew;
+                    }
+                    ws[8] += (double)__popc(mbad);
                 }
                 if (mres) {   // once per episode
                     const int s_len = __reduce_add_sync(FULL, ep_len_done);

@@ -72,7 +72,7 @@ def test_decoupled_full_size_invariants_and_env_swap():
     assert bool(torch.isfinite(o).all()) and bool((o[:, 0:3].abs() < 1).all()) and bool((o[:, 6:9].abs() < 1).all())
     R = ea.state_soa[6:15].t().reshape(n, 3, 3)
     assert float((R @ R.transpose(1, 2) - torch.eye(3, device="cuda:0")).abs().max()) < 1e-3
-    assert abs(sa[16] - sb[16]) <= 1e-6 * sb[16] and 0 < sa[16] < sa[7]          # sum of benchmark rewards in (0, steps)
+    assert sa[16] == sb[16] == 0 and sa[14] == 0                                 # per-step sums are kept with diagnostics only
     ea.close(); eb.close()
 
 
