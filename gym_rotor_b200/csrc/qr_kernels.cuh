@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             {
                 const int att = (nf - 2) / 12;
                 const int s_nfev = __reduce_add_sync(FULL, nf);
-                const int s_proj = __reduce_add_sync(FULL, nproj);
+                const int s_proj = c.diagnostics ? __reduce_add_sync(FULL, nproj) : 0;   // (a per-step sum: with diagnostics only)
                 // per-step sums -- attempt histogram, reward, benchmark reward -- with diagnostics only (kernel-uniform); the mean
                 // attempt count is always available from the nfev sum (2 + 12 per attempt), returns from the episode statistics
                 unsigned m1 = 0, m2 = 0, m3 = 0, m4 = 0;
@@ -575,12 +575,13 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 const unsigned mres = __ballot_sync(FULL, ep_done);
                 if (lane == 0) {
                     if (MODE != 0 && msolved) ws[17] += (double)__popc(msolved);
-                    ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev; ws[15] += (double)s_proj;
+                    ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev;
                     if (c.diagnostics) {
+                        ws[15] += (double)s_proj;
                         ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
                         ws[14] += (double)s_rew; ws[16] += (double)s_brew;
                     }
-                    ws[8] += (double)__popc(mbad);
+                    if (mbad) ws[8] += (double)__popc(mbad);
                 }
                 if (mres) {   // once per episode
                     const int s_len = __reduce_add_sync(FULL, ep_len_done);

@@ -24,8 +24,9 @@ namespace qr {
 // tie the persistent state to that grouping, which conflicts with the integrator's register pairs (qr_dop853.cuh) and
 // costs moves in every stage instead of once per step.
 #if QR_PTX
-QR_DEV float own_reg(float v) { float r; asm volatile("mov.b32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
-QR_DEV double own_reg(double v) { double r; asm volatile("mov.b64 %0, %1;" : "=d"(r) : "d"(v)); return r; }
+// (not volatile: a copy nobody reads -- the attitude entries of an observation row that is not stored -- may be dropped)
+QR_DEV float own_reg(float v) { float r; asm("mov.b32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+QR_DEV double own_reg(double v) { double r; asm("mov.b64 %0, %1;" : "=d"(r) : "d"(v)); return r; }
 #else
 QR_DEV float own_reg(float v) { return v; }
 QR_DEV double own_reg(double v) { return v; }

@@ -76,7 +76,7 @@ typedef struct qr_config {
     int32_t env_type;           /* QR_ENV_* used by in-kernel auto resets */
     int32_t max_episode_steps;  /* truncation limit (main.py:169, args_parse.py:16); 0 = none */
     int32_t reserved0;          /* diagnostics (default 1): write nfev per env and keep the per-step statistics ATTEMPTS_*, REWARD0,
-                                 * BENCH_REWARD (0: they stay zero; the mean attempt count is (NFEV / STEPS - 2) / 12) */
+                                 * BENCH_REWARD, SO3_PROJECTIONS (0: they stay zero; the mean attempt count is (NFEV / STEPS - 2) / 12) */
     int32_t round_returns;      /* 1: running episode returns are rounded to 4 decimals after every step, as the trainer
                                  * keeps them (main.py:180); 0: plain sums */
     int32_t reserved1;
