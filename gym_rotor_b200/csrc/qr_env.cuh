@@ -25,6 +25,10 @@ template <> struct rn<float> {
     // division by a launch constant: multiply by its host-computed reciprocal (float32 mode is not the
     // bit-parity mode; the float64 instantiation below keeps numpy's exact quotient)
     static QR_DEV float divc(float a, float b, float inv_b) { (void)b; return __fmul_rn(a, inv_b); }
+    // a b + c d: WHICH product is fused is spelled out -- left to the compiler it depends on the use counts of the products,
+    // i.e. on the kernel instantiation, and multi-step and single-step launches must agree bit for bit
+    static QR_DEV float dot2(float a, float b, float c, float d) { return fmaf(a, b, __fmul_rn(c, d)); }
+    static QR_DEV float madd(float a, float b, float c) { return fmaf(a, b, c); }   // a b + c, likewise
 };
 template <> struct rn<double> {
     static QR_DEV double mul(double a, double b) { return __dmul_rn(a, b); }
@@ -32,6 +36,8 @@ template <> struct rn<double> {
     static QR_DEV double sub(double a, double b) { return __dsub_rn(a, b); }
     static QR_DEV double div(double a, double b) { return __ddiv_rn(a, b); }
     static QR_DEV double divc(double a, double b, double inv_b) { (void)inv_b; return __ddiv_rn(a, b); }
+    static QR_DEV double dot2(double a, double b, double c, double d) { return __dadd_rn(__dmul_rn(a, b), __dmul_rn(c, d)); }
+    static QR_DEV double madd(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }
 };
 
 // ---- kernel arguments --------------------------------------------------------------------------------
@@ -212,7 +218,7 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
     T d3 = N::fma(b1d[2], b3[2], N::fma(b1d[1], b3[1], A::mul(b1d[0], b3[0])));
     T b1c[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) b1c[i] = A::sub(b1d[i], A::mul(d3, b3[i]));
+    for (int i = 0; i < 3; ++i) b1c[i] = A::madd(-d3, b3[i], b1d[i]);
     T dn = N::fma(b1c[2], b2[2], N::fma(b1c[1], b2[1], A::mul(b1c[0], b2[0])));
     T dd = N::fma(b1c[2], b1[2], N::fma(b1c[1], b1[1], A::mul(b1c[0], b1[0])));
     const T PI = (T)3.14159265358979323846;
@@ -220,15 +226,15 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
     T eIxn[3], eIb1n;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        T gnew = A::add(A::mul(-c.alpha, e.I[i]), A::mul(ex[i], c.x_lim));
-        e.I[i] = A::add(e.I[i], A::mul(A::mul(A::add(e.I[3 + i], gnew), c.dt), (T)0.5));
+        T gnew = A::dot2(-c.alpha, e.I[i], ex[i], c.x_lim);
+        e.I[i] = A::madd(A::mul(A::add(e.I[3 + i], gnew), c.dt), (T)0.5, e.I[i]);
         e.I[3 + i] = gnew;
         T q = A::divc(e.I[i], c.eIx_lim, c.inv_eIx_lim);
         eIxn[i] = q < -c.sat ? -c.sat : (q > c.sat ? c.sat : q);
     }
     {
-        T gnew = A::add(A::mul(-c.beta, e.I[6]), A::mul(eb1n, PI));
-        e.I[6] = A::add(e.I[6], A::mul(A::mul(A::add(e.I[7], gnew), c.dt), (T)0.5));
+        T gnew = A::dot2(-c.beta, e.I[6], eb1n, PI);
+        e.I[6] = A::madd(A::mul(A::add(e.I[7], gnew), c.dt), (T)0.5, e.I[6]);
         e.I[7] = gnew;
         T q = A::divc(e.I[6], c.eIb1_lim, c.inv_eIb1_lim);
         eIb1n = q < -c.sat ? -c.sat : (q > c.sat ? c.sat : q);
@@ -237,7 +243,7 @@ template <typename T> QR_DEV int norm_error_state(EnvRegs<T>& e, const EnvConst<
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             o[i] = (float)ex[i]; o[3 + i] = (float)eIxn[i]; o[6 + i] = (float)ev[i]; o[9 + i] = own_reg((float)b3[i]);
-            o[12 + i] = (float)A::add(A::mul(eW[0], b1[i]), A::mul(eW[1], b2[i]));
+            o[12 + i] = (float)A::dot2(eW[0], b1[i], eW[1], b2[i]);
         }
         o[15] = (float)eb1n; o[16] = (float)eIb1n; o[17] = (float)eW[2];
     } else {
@@ -279,20 +285,21 @@ QR_DEV double interp01(double r, double rmin, double slope)
 }
 
 // float32 mode: the same interpolation in float32 (no trip through the FP64 pipe)
+// (two selects, no branch; a NaN r fails both comparisons and comes back through the product)
 QR_DEV float interp01f(float r, float rmin, float slope)
 {
-    if (r != r) return r;
-    if (r <= rmin) return 0.0f;
-    if (r >= 0.0f) return 1.0f;
-    return slope * (r - rmin);
+    float v = slope * (r - rmin);
+    v = (r >= 0.0f) ? 1.0f : v;
+    return (r <= rmin) ? 0.0f : v;
 }
-template <typename T> QR_DEV double interp01t(float r, double rmin, double slope)
+template <typename T> QR_DEV T interp01t(float r, double rmin, double slope)
 {
-    if (sizeof(T) == 8) return interp01((double)r, rmin, slope);
-    return (double)interp01f(r, (float)rmin, (float)slope);
+    if (sizeof(T) == 8) return (T)interp01((double)r, rmin, slope);
+    return (T)interp01f(r, (float)rmin, (float)slope);
 }
 
-template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float* o, double* rew, int* dn, const int mode)
+// RT: the type the reward is handed on in -- T in the step kernel (float32 mode: no trip through the FP64 pipe), double elsewhere
+template <typename T, typename RT> QR_DEV void reward_done(const EnvConst<T>& c, const float* o, RT* rew, int* dn, const int mode)
 {
     dn[0] = 0; dn[1] = 0;
     if (mode == 1) {
@@ -304,8 +311,8 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
 #pragma unroll
         for (int i = 0; i < 3; ++i)
             if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[20 + i]) >= 1.0f) dn[0] = 1;
-        rew[0] = dn[0] ? -1.0 : interp01t<T>(r, c.rmin, c.slope);
-        rew[1] = 0.0;
+        rew[0] = dn[0] ? (RT)-1 : (RT)interp01t<T>(r, c.rmin, c.slope);
+        rew[1] = 0;
     } else {
         float rx = __fmul_rn(c.nCx, norm2sq_f32<sizeof(T) == 8>(o)), rix = __fmul_rn(c.nCIx, norm2sq_f32<sizeof(T) == 8>(o + 3));
         float rv = __fmul_rn(c.nCv, norm2sq_f32<sizeof(T) == 8>(o + 6)), rw = __fmul_rn(c.nCw12, norm2sq_f32<sizeof(T) == 8>(o + 12));
@@ -317,8 +324,8 @@ template <typename T> QR_DEV void reward_done(const EnvConst<T>& c, const float*
         for (int i = 0; i < 3; ++i)
             if (fabsf(o[i]) >= 1.0f || fabsf(o[6 + i]) >= 1.0f || fabsf(o[12 + i]) >= 1.0f) dn[0] = 1;
         if (a2 >= 1.0f) dn[1] = 1;
-        rew[0] = dn[0] ? -1.0 : interp01t<T>(r1, c.rmin1, c.slope1);
-        rew[1] = dn[1] ? -1.0 : interp01t<T>(r2, c.rmin2, c.slope2);
+        rew[0] = dn[0] ? (RT)-1 : (RT)interp01t<T>(r1, c.rmin1, c.slope1);
+        rew[1] = dn[1] ? (RT)-1 : (RT)interp01t<T>(r2, c.rmin2, c.slope2);
     }
 }
 
@@ -386,14 +393,14 @@ QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, 
                 tv = tv < (float)c.min_force ? (float)c.min_force : (tv > (float)maxf ? (float)maxf : tv);
                 Tm[i] = (T)tv;
             } else {
-                T tv = A::add(A::mul(scale, a[i]), avrg);
+                T tv = A::madd(scale, a[i], avrg);
                 Tm[i] = tv < c.min_force ? c.min_force : (tv > maxf ? maxf : tv);
             }
         }
         f = A::add(A::add(A::add(Tm[0], Tm[1]), Tm[2]), Tm[3]);   // forces_to_fM @ T, quad.py:396-401,238
-        M[0] = A::add(A::mul(-e.d, Tm[1]), A::mul(e.d, Tm[3]));
-        M[1] = A::add(A::mul(e.d, Tm[0]), A::mul(-e.d, Tm[2]));
-        M[2] = A::add(A::add(A::add(A::mul(-e.c_tf, Tm[0]), A::mul(e.c_tf, Tm[1])), A::mul(-e.c_tf, Tm[2])), A::mul(e.c_tf, Tm[3]));
+        M[0] = A::dot2(-e.d, Tm[1], e.d, Tm[3]);
+        M[1] = A::dot2(e.d, Tm[0], -e.d, Tm[2]);
+        M[2] = A::madd(e.c_tf, Tm[3], A::madd(-e.c_tf, Tm[2], A::dot2(-e.c_tf, Tm[0], e.c_tf, Tm[1])));
         return;
     }
     if (act_f32 && sizeof(T) == 8) {
@@ -402,7 +409,7 @@ QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, 
         fv = fv < lo ? lo : (fv > hi ? hi : fv);
         f = (T)fv;
     } else {
-        T fv = A::mul((T)4, A::add(A::mul(scale, a[0]), avrg));
+        T fv = A::mul((T)4, A::madd(scale, a[0], avrg));
         T lo = A::mul((T)4, c.min_force), hi = A::mul((T)4, maxf);
         f = fv < lo ? lo : (fv > hi ? hi : fv);
     }
@@ -413,8 +420,8 @@ QR_DEV void action_to_fM(const EnvRegs<T>& e, const EnvConst<T>& c, const T* a, 
         const T* b1 = e.y + 3; const T* b2 = e.y + 6;
         T t1 = N::fma(b1[2], a[3], N::fma(b1[1], a[2], A::mul(b1[0], a[1])));
         T t2 = N::fma(b2[2], a[3], N::fma(b2[1], a[2], A::mul(b2[0], a[1])));
-        M[0] = A::add(t1, A::mul(A::mul(e.J3, e.W3), e.y[13]));
-        M[1] = A::sub(t2, A::mul(A::mul(e.J3, e.W3), e.y[12]));
+        M[0] = A::madd(A::mul(e.J3, e.W3), e.y[13], t1);
+        M[1] = A::madd(-A::mul(e.J3, e.W3), e.y[12], t2);
         M[2] = a[4];
     }
 }

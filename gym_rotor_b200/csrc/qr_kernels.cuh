@@ -118,6 +118,23 @@ QR_DEV void cp_async_wait_all() {}
 QR_DEV void cp_async_commit() {}
 template <int N> QR_DEV void cp_async_wait_group() {}
 #endif
+// Stores behind a predicate that can never become a branch.  The warp runs phase A with three warps per scheduler and
+// nothing to hide a fetch redirect behind: every TAKEN branch on the common path (a skipped option, a skipped rare case)
+// measured ~0.3 % of the launch, about ten instructions' worth (profiles/r02/r02ap_taken_branches.txt).
+#if QR_PTX
+QR_DEV void st_if(bool p, float* g, float v) { asm volatile("{ .reg .pred q; setp.ne.s32 q, %0, 0; @q st.global.f32 [%1], %2; }" ::"r"((int)p), "l"(g), "f"(v) : "memory"); }
+QR_DEV void st_if(bool p, double* g, double v) { asm volatile("{ .reg .pred q; setp.ne.s32 q, %0, 0; @q st.global.f64 [%1], %2; }" ::"r"((int)p), "l"(g), "d"(v) : "memory"); }
+QR_DEV void sts_if(bool p, double* s, double v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.f64 [%1], %2; }" ::"r"((int)p), "r"((unsigned)__cvta_generic_to_shared(s)), "d"(v) : "memory");
+}
+template <int N> QR_DEV void cp_async_wait_group_if(bool p) { asm volatile("{ .reg .pred q; setp.ne.s32 q, %0, 0; @q cp.async.wait_group %1; }" ::"r"((int)p), "n"(N) : "memory"); }
+#else
+QR_DEV void st_if(bool p, float* g, float v) { if (p) *g = v; }
+QR_DEV void st_if(bool p, double* g, double v) { if (p) *g = v; }
+QR_DEV void sts_if(bool p, double* s, double v) { if (p) *s = v; }
+template <int N> QR_DEV void cp_async_wait_group_if(bool) {}
+#endif
 template <typename T> QR_DEV int32_t& stash_i32(T* sh, int slot) { return *reinterpret_cast<int32_t*>(sh + slot * 32); }
 
 // ---- auto reset, out of line (rare: once per episode) ---------------------------------------------------------
@@ -374,24 +391,27 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             cp_async_commit();
         }
         // ---- A1: finish the env.step that just completed ----
+        // One test per lane for everything that does not happen on every sub-step of a multi-step launch (rows and scalar
+        // outputs of the last sub-step, caller's rollout storage, the end of an episode, the release of the env, a status
+        // flag, rounded returns), one warp-uniform test for what follows it (rows of a lock-step warp, the reset queue,
+        // episode statistics, diagnostics); what every step needs is straight-line code.  Single-step launches take the
+        // first block unconditionally (`last` and `!stay` are compile-time constants there).
         if (finmask) {
             __syncwarp();   // phase B is over for every lane: the stage storage may be reused as reset scratch
             bool ep_done = false, term = false, trunc = false;
             int nf = 0, st = 0, nproj = 0, ep_len_done = 0;
-            float rew0f = 0.f, brew = 0.f;
+            float rew0f = 0.f;
+            float bex0 = 0.f, bex1 = 0.f, bex2 = 0.f, beb1 = 0.f;   // what benchmark_reward_func reads (diagnostics)
             bool solved = false;
             T ret_done0 = 0, ret_done1 = 0;
-            T In[8];                    // integral errors after this step
-            T ep_ret0 = 0, ep_ret1 = 0; // episode accumulators after this step
-            int ep_len = 0;
-            uint32_t ep_idx = 0;
-            float *obs1 = nullptr, *obs2 = nullptr;   // where this step's observation row goes
+            const bool finl = fin;
             const bool last = (k == NS - 1);
             // all 32 lanes finish the same sub-step of 32 consecutive envs, first one 4-aligned (16-byte aligned rows block)
             const int64_t e_first = __shfl_sync(FULL, e, 0);
             const int k_first = __shfl_sync(FULL, k, 0);
             const bool same = __all_sync(FULL, e - lane == e_first && k == k_first);   // (no warp primitive behind a short-circuit)
-            const bool coop = finmask == FULL && same && !a.obs_roll;   // padded rows are 16-byte aligned; dense rollout rows: per lane
+            // padded rows are 16-byte aligned; dense rollout rows: per lane.  (`same` makes `last` warp-uniform.)
+            const bool coop = finmask == FULL && same && !(MULTI && a.obs_roll) && (last || POLICY);
             if (fin) {
                 float o[23];
                 st = ode.status; nf = ode.nfev; nproj = ode.nproj;
@@ -404,10 +424,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 r.W3 = W3;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r.I[i] = sh[(S_I + i) * 32];
-                ep_ret0 = sh[S_RET0 * 32];
+                T ep_ret0 = sh[S_RET0 * 32], ep_ret1 = 0;   // episode accumulators
                 if (G == 2) ep_ret1 = sh[S_RET1 * 32];
-                ep_len = stash_i32(sh, S_LEN);
-                ep_idx = (uint32_t)stash_i32(sh, S_IDX);
+                int ep_len = stash_i32(sh, S_LEN);
+                uint32_t ep_idx = (uint32_t)stash_i32(sh, S_IDX);
                 if (GOAL1) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) { r.goal[i] = 0; r.goal[3 + i] = 0; r.goal[6 + i] = sh[(S_B1D + i) * 32]; r.goal[9 + i] = sh[(S_WD + i) * 32]; }
@@ -420,170 +440,171 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
 #pragma unroll
                     for (int i = 0; i < 12; ++i) r.goal[i] = a.goal[i * N + e];
                 }
-                double rew[2]; int dn[2];
+                T rew[2]; int dn[2];   // (float32 mode: the reward is a float32 value anyway)
                 if (MODE == 0) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) o[i] = (float)x[i];
 #pragma unroll
                     for (int i = 0; i < 12; ++i) o[3 + i] = (float)y[i];
                     o[15] = (float)y[12]; o[16] = (float)y[13]; o[17] = (float)W3;
-                    reward_done_quad<T>(r, c, rew, dn);
+                    double rq[2];
+                    reward_done_quad<T>(r, c, rq, dn);
+                    rew[0] = (T)rq[0]; rew[1] = (T)rq[1];
                 } else {
                     int fl = norm_error_state<T>(r, c, o, MODE);
                     if (fl & 2) st |= 4;
                     if (MULTI) r_ok = (fl == 0);
-                    reward_done<T>(c, o, rew, dn, MODE);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) In[i] = r.I[i];
-                // ---- the observation row leaves the registers at once.  General case: each lane writes its own row
-                // (scattered 4-byte stores; the rows of neighbouring lanes are adjacent in memory, so L2 assembles
-                // full sectors; measured 5 % faster than a general coalescing copy through shared memory).  When the
-                // whole warp finishes 32 consecutive envs together (`coop`: the lock-step regime of a trained
-                // policy), the rows go through a shared tile and leave as 16-byte stores of one contiguous block.
-                if (a.obs_roll) {   // kernel-uniform: caller's rollout storage (dense rows), plus the handle's row where it is read back
-                    obs1 = a.obs_roll + ((int64_t)k * N + e) * O;
-                    if (last || POLICY) obs2 = a.obs + e * OS;   // POLICY: the actor reads a.obs at the next sub-step
-                } else if (last || POLICY) obs1 = a.obs + e * OS;
-                if (coop || (POLICY && MULTI)) {
-                    // (policy rollouts: the actor of the next sub-step reads the row from here, not from HBM -- unless a reset
-                    //  batch reuses the stage storage in between, see A3)
-                    float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
-#pragma unroll
-                    for (int i = 0; i < OS / 4; ++i)
-                        reinterpret_cast<float4*>(tile + lane * OS)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], (4 * i + 3 < O) ? o[4 * i + 3] : 0.f);
-                    if (POLICY && MULTI) obs_in_tile = true;
-                }
-                if (!coop) {
-                    {   // rows inside a.obs are 16-byte aligned and padded: vector stores; caller's rollout storage: scalar
-                        float op[OS];
-#pragma unroll
-                        for (int i = 0; i < OS; ++i) op[i] = (i < O) ? o[i] : 0.f;
-                        float* rows[2] = {obs1, obs2};
-#pragma unroll
-                        for (int w = 0; w < 2; ++w) {
-                            float* row = rows[w];
-                            if (!row) continue;
-                            if (a.obs_roll && w == 0) {
-#pragma unroll
-                                for (int i = 0; i < O; ++i) row[i] = o[i];
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < OS / 4; ++i)
-                                    reinterpret_cast<float4*>(row)[i] = make_float4(op[4 * i], op[4 * i + 1], op[4 * i + 2], op[4 * i + 3]);
-                            }
-                        }
-                    }
+                    reward_done<T, T>(c, o, rew, dn, MODE);
                 }
                 rew0f = (float)rew[0];
-                if (c.round_returns) {   // the trainer's running return, main.py:180: float('{:.4f}'.format(ret + r)) every step
-                    ep_ret0 = (T)(rint(((double)ep_ret0 + rew[0]) * 1e4) / 1e4);   // k / 10^4 correctly rounded = float('0.dddd')
-                    if (G == 2) ep_ret1 = (T)(rint(((double)ep_ret1 + rew[1]) * 1e4) / 1e4);
-                } else {
-                    ep_ret0 += (T)rew[0];
-                    if (G == 2) ep_ret1 += (T)rew[1];
-                }
+                T ret0 = ep_ret0 + rew[0], ret1 = (G == 2) ? ep_ret1 + rew[1] : (T)0;   // (rounded returns: replaced below)
                 ep_len += 1;
                 term = (dn[0] | dn[1]) != 0;
                 trunc = c.max_episode_steps > 0 && ep_len >= c.max_episode_steps;
                 if (MODE != 0) {
                     // benchmark_reward_func(ex, eb1) = interp(-|ex| - |eb1|, [-2, 0], [0, 1]) (utils/utils.py:21-47) on this
-                    // step's observation (a per-step statistic: with diagnostics only), and the trainer's "solved" relabel at
-                    // the time limit (main.py:169-173)
-                    const float ex0 = o[0] * (float)c.x_lim, ex1 = o[1] * (float)c.x_lim, ex2 = o[2] * (float)c.x_lim;
-                    if (c.diagnostics) {
-                        const float eb1 = o[MODE == 1 ? 18 : 15] * 3.14159265358979f;
-                        const float rb = -sqrtf(fmaf(ex2, ex2, fmaf(ex1, ex1, ex0 * ex0))) - fabsf(eb1);
-                        brew = fminf(fmaxf(fmaf(rb, 0.5f, 1.0f), 0.f), 1.f);
+                    // step's observation (a per-step statistic: with diagnostics only, evaluated in the statistics block), and
+                    // the trainer's "solved" relabel at the time limit (main.py:169-173)
+                    bex0 = o[0] * (float)c.x_lim; bex1 = o[1] * (float)c.x_lim; bex2 = o[2] * (float)c.x_lim;
+                    beb1 = o[MODE == 1 ? 18 : 15];
+                    solved = trunc && fabsf(bex0) <= 0.03f && fabsf(bex1) <= 0.03f && fabsf(bex2) <= 0.03f && rew[0] != (T)-1;
+                }
+                const bool epd = c.autoreset && (term || trunc);
+                const bool stay = MULTI && k + 1 < NS && !epd;   // the env keeps its lane for the next sub-step
+                const bool want_row = last || POLICY || (MULTI && a.obs_roll);
+                if (want_row || !stay || st != 0 || c.round_returns || (MULTI && (a.reward_roll || a.done_roll))) {
+                    if (c.round_returns) {   // the trainer's running return, main.py:180: float('{:.4f}'.format(ret + r)) every step
+                        ret0 = (T)(rint(((double)ep_ret0 + (double)rew[0]) * 1e4) / 1e4);   // k / 10^4 correctly rounded = float('0.dddd')
+                        if (G == 2) ret1 = (T)(rint(((double)ep_ret1 + (double)rew[1]) * 1e4) / 1e4);
                     }
-                    solved = trunc && fabsf(ex0) <= 0.03f && fabsf(ex1) <= 0.03f && fabsf(ex2) <= 0.03f && rew[0] != -1.0;
-                }
-                // per-step scalar outputs
-                if (a.reward_roll) {   // (kernel-uniform)
-                    T* rw = a.reward_roll + ((int64_t)k * N + e) * G;
-                    rw[0] = (T)rew[0]; if (G == 2) rw[1] = (T)rew[1];
-                }
-                if (a.done_roll) {
-                    uint8_t* dd = a.done_roll + ((int64_t)k * N + e) * G;
-                    dd[0] = (uint8_t)dn[0]; if (G == 2) dd[1] = (uint8_t)dn[1];
-                }
-                if (last) {
-                    a.reward[e * G] = (T)rew[0]; if (G == 2) a.reward[e * G + 1] = (T)rew[1];
-                    a.done[e * G] = (uint8_t)dn[0]; if (G == 2) a.done[e * G + 1] = (uint8_t)dn[1];
-                }
-                if (last) { a.terminated[e] = (uint8_t)term; a.truncated[e] = (uint8_t)trunc; }
-                if (c.diagnostics && last) a.nfev[e] = nf;
-                if (st) a.status[e] |= (uint8_t)st;
-                if (c.autoreset && (term || trunc)) {
-                    ep_len_done = ep_len; ret_done0 = ep_ret0; ret_done1 = ep_ret1;
+                    // ---- the observation row.  General case: each lane writes its own row (the rows of neighbouring lanes
+                    // are adjacent in memory, so L2 assembles full sectors; measured 5 % faster than a general coalescing
+                    // copy through shared memory).  When the whole warp finishes 32 consecutive envs together (`coop`: the
+                    // lock-step regime of a trained policy), the rows go through a shared tile and leave as 16-byte stores
+                    // of one contiguous block.
+                    if (want_row) {
+                        float *obs1 = nullptr, *obs2 = nullptr;   // where this step's observation row goes
+                        if (MULTI && a.obs_roll) {   // kernel-uniform: caller's rollout storage (dense rows), plus the handle's row where it is read back
+                            obs1 = a.obs_roll + ((int64_t)k * N + e) * O;
+                            if (last || POLICY) obs2 = a.obs + e * OS;   // POLICY: the actor reads a.obs at the next sub-step
+                        } else obs1 = a.obs + e * OS;
+                        if (coop || (POLICY && MULTI)) {
+                            // (policy rollouts: the actor of the next sub-step reads the row from here, not from HBM -- unless a
+                            //  reset batch reuses the stage storage in between, see A3)
+                            float* tile = reinterpret_cast<float*>(ks);   // the stage storage is free in phase A
+#pragma unroll
+                            for (int i = 0; i < OS / 4; ++i)
+                                reinterpret_cast<float4*>(tile + lane * OS)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], (4 * i + 3 < O) ? o[4 * i + 3] : 0.f);
+                            if (POLICY && MULTI) obs_in_tile = true;
+                        }
+                        if (!coop) {   // rows inside a.obs are 16-byte aligned and padded: vector stores; caller's rollout storage: scalar
+                            float op[OS];
+#pragma unroll
+                            for (int i = 0; i < OS; ++i) op[i] = (i < O) ? o[i] : 0.f;
+                            float* rows[2] = {obs1, obs2};
+#pragma unroll
+                            for (int w = 0; w < 2; ++w) {
+                                float* row = rows[w];
+                                if (!row) continue;
+                                if (MULTI && a.obs_roll && w == 0) {
+#pragma unroll
+                                    for (int i = 0; i < O; ++i) row[i] = o[i];
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < OS / 4; ++i)
+                                        reinterpret_cast<float4*>(row)[i] = make_float4(op[4 * i], op[4 * i + 1], op[4 * i + 2], op[4 * i + 3]);
+                                }
+                            }
+                        }
+                    }
+                    // per-step scalar outputs
+                    if (MULTI && a.reward_roll) {   // (kernel-uniform)
+                        T* rw = a.reward_roll + ((int64_t)k * N + e) * G;
+                        rw[0] = rew[0]; if (G == 2) rw[1] = rew[1];
+                    }
+                    if (MULTI && a.done_roll) {
+                        uint8_t* dd = a.done_roll + ((int64_t)k * N + e) * G;
+                        dd[0] = (uint8_t)dn[0]; if (G == 2) dd[1] = (uint8_t)dn[1];
+                    }
                     if (last) {
+                        a.reward[e * G] = rew[0]; if (G == 2) a.reward[e * G + 1] = rew[1];
+                        a.done[e * G] = (uint8_t)dn[0]; if (G == 2) a.done[e * G + 1] = (uint8_t)dn[1];
+                        a.terminated[e] = (uint8_t)term; a.truncated[e] = (uint8_t)trunc;
+                        if (c.diagnostics) a.nfev[e] = nf;
+                        if (epd) {
 #pragma unroll
-                        for (int i = 0; i < O; ++i) a.final_obs[e * OS + i] = o[i];
+                            for (int i = 0; i < O; ++i) a.final_obs[e * OS + i] = o[i];
+                        }
                     }
-                    ep_idx += 1;
-                    ep_ret0 = 0; ep_ret1 = 0; ep_len = 0;
-                    ep_done = true;
-                }
-            }
-            if (coop) {
-                __syncwarp();
-                const float4* tile4 = reinterpret_cast<const float4*>(ks);
-                constexpr int NV = 32 * OS / 4;   // float4 elements of the 32-row block (rows padded)
-                float4* g1 = reinterpret_cast<float4*>((last || POLICY) ? a.obs + e_first * OS : nullptr);
-                float4* g2 = nullptr;
+                    if (st) a.status[e] |= (uint8_t)st;
+                    if (!stay) {
+                        // release the env: state back to HBM -- but not the terminal state of an env whose reset is queued (the
+                        // reset writes the new one; in a multi-step launch another lane then goes on stepping it, see CQ)
+                        if (!epd) {
 #pragma unroll
-                for (int it = 0; it < (NV + 31) / 32; ++it) {
-                    const int q = it * 32 + lane;
-                    if (q < NV) {
-                        const float4 v = tile4[q];
-                        if (g1) g1[q] = v;
-                        if (g2) g2[q] = v;
+                            for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
+#pragma unroll
+                            for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
+                            a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) a.integ[i * N + e] = r.I[i];
+                        }
+                        a.ep_return[e] = epd ? (T)0 : ret0;
+                        if (G == 2) a.ep_return[N + e] = epd ? (T)0 : ret1;
+                        a.ep_length[e] = epd ? 0 : ep_len;
+                        a.ep_index[e] = ep_idx + (epd ? 1u : 0u);
+                        busy = false;
                     }
                 }
-                __syncwarp();
-            }
-            // ---- auto reset: only noted here, carried out further down (see `parked reset`).  Single-step launches
-            // queue the env (it leaves the lane anyway) so that a whole batch is reset at once. ----
-            {
-                const unsigned wmask = __ballot_sync(FULL, ep_done);
-                if (wmask) {   // RQ holds 64: at most QR_RESET_BATCH - 1 entries from earlier rounds + 32 new ones
-                    if (ep_done) {
-                        const int q = rq_n + __popc(wmask & ((1u << lane) - 1u));
-                        rq[q] = (int32_t)e; if (MULTI) rqk[q] = (int16_t)(k + 1);   // the env goes on at sub-step k + 1 (multi-step launches)
-                    }
-                    rq_n += __popc(wmask);
+                // the end of an episode, without a branch: only noted here, the reset is carried out further down
+                ep_done = epd;
+                ep_len_done = epd ? ep_len : 0; ret_done0 = epd ? ret0 : (T)0; ret_done1 = epd ? ret1 : (T)0;
+                fin = false;
+                if (MULTI) k += 1;
+                need_init = stay;
+                if (stay) {   // end-of-step values back into the stash
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sh[(S_I + i) * 32] = r.I[i];
+                    sh[S_RET0 * 32] = ret0;
+                    if (G == 2) sh[S_RET1 * 32] = ret1;
+                    stash_i32(sh, S_LEN) = ep_len;
+                    stash_i32(sh, S_IDX) = (int32_t)ep_idx;
                 }
             }
-            __syncwarp();
-            // ---- statistics of the finished lanes: votes and REDUX, accumulated by lane 0 in shared memory ----
+            // ---- statistics of the finished lanes: votes and REDUX; lane 0 accumulates in shared memory (every lane forms
+            // the sums, one stores: no divergent region) ----
+            const unsigned mres = __ballot_sync(FULL, ep_done);
             {
-                const int att = (nf - 2) / 12;
                 const int s_nfev = __reduce_add_sync(FULL, nf);
-                const int s_proj = c.diagnostics ? __reduce_add_sync(FULL, nproj) : 0;   // (a per-step sum: with diagnostics only)
-                // per-step sums -- attempt histogram, reward, benchmark reward -- with diagnostics only (kernel-uniform); the mean
-                // attempt count is always available from the nfev sum (2 + 12 per attempt), returns from the episode statistics
-                unsigned m1 = 0, m2 = 0, m3 = 0, m4 = 0;
-                float s_rew = 0.f, s_brew = 0.f;
-                if (c.diagnostics) {
-                    m1 = __ballot_sync(FULL, fin && att == 1); m2 = __ballot_sync(FULL, fin && att == 2);
-                    m3 = __ballot_sync(FULL, fin && att == 3); m4 = __ballot_sync(FULL, fin && att >= 4);
-                    s_rew = warp_sum_f(rew0f);
-                    if (MODE != 0) s_brew = warp_sum_f(brew);
-                }
-                const unsigned mbad = __ballot_sync(FULL, fin && st != 0);
+                const unsigned mbad = __ballot_sync(FULL, finl && st != 0);
                 const unsigned msolved = (MODE != 0) ? __ballot_sync(FULL, solved) : 0u;
-                const unsigned mres = __ballot_sync(FULL, ep_done);
-                if (lane == 0) {
-                    if (MODE != 0 && msolved) ws[17] += (double)__popc(msolved);
-                    ws[7] += (double)__popc(finmask); ws[9] += (double)s_nfev;
-                    if (c.diagnostics) {
-                        ws[15] += (double)s_proj;
-                        ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
-                        ws[14] += (double)s_rew; ws[16] += (double)s_brew;
+                const bool l0 = lane == 0;
+                sts_if(l0, ws + 7, ws[7] + (double)__popc(finmask));
+                sts_if(l0, ws + 9, ws[9] + (double)s_nfev);
+                sts_if(l0, ws + 8, ws[8] + (double)__popc(mbad));
+                if (MODE != 0) sts_if(l0, ws + 17, ws[17] + (double)__popc(msolved));
+            }
+            if (coop || mres != 0 || c.diagnostics) {   // (warp-uniform)
+                if (coop) {
+                    __syncwarp();
+                    const float4* tile4 = reinterpret_cast<const float4*>(ks);
+                    constexpr int NV = 32 * OS / 4;   // float4 elements of the 32-row block (rows padded)
+                    float4* g1 = reinterpret_cast<float4*>(a.obs + e_first * OS);
+#pragma unroll
+                    for (int it = 0; it < (NV + 31) / 32; ++it) {
+                        const int q = it * 32 + lane;
+                        if (q < NV) g1[q] = tile4[q];
                     }
-                    if (mbad) ws[8] += (double)__popc(mbad);
+                    __syncwarp();
                 }
                 if (mres) {   // once per episode
+                    // auto reset: single-step launches queue the env too (it leaves the lane anyway), so that a whole batch is
+                    // reset at once.  RQ holds 64: at most QR_RESET_BATCH - 1 entries from earlier rounds + 32 new ones
+                    if (ep_done) {
+                        const int q = rq_n + __popc(mres & ((1u << lane) - 1u));
+                        rq[q] = (int32_t)e; if (MULTI) rqk[q] = (int16_t)k;   // the env goes on at the next sub-step (k: already advanced)
+                    }
+                    rq_n += __popc(mres);
                     const int s_len = __reduce_add_sync(FULL, ep_len_done);
                     const unsigned mterm = __ballot_sync(FULL, ep_done && term);
                     const double r0 = (double)warp_sum_f(ep_done ? (float)ret_done0 : 0.f);
@@ -594,37 +615,28 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         ws[5] += (double)(__popc(mres) - __popc(mterm)); ws[1] += r0; ws[2] += r1; ws[6] += r0sq;
                     }
                 }
-            }
-            if (fin) {
-                fin = false;
-                if (MULTI) k += 1;
-                if (MULTI && k < NS && !ep_done) {
-                    need_init = true;   // the env stays in this lane: end-of-step values back into the stash
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sh[(S_I + i) * 32] = In[i];
-                    sh[S_RET0 * 32] = ep_ret0;
-                    if (G == 2) sh[S_RET1 * 32] = ep_ret1;
-                    stash_i32(sh, S_LEN) = ep_len;
-                    stash_i32(sh, S_IDX) = (int32_t)ep_idx;
-                } else {
-                    // release the env: state back to HBM -- but not the terminal state of an env whose reset is queued (the
-                    // reset writes the new one; in a multi-step launch another lane then goes on stepping it, see CQ)
-                    if (!ep_done) {
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) a.state[i * N + e] = x[i];
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) a.state[(3 + i) * N + e] = y[i];
-                        a.state[15 * N + e] = y[12]; a.state[16 * N + e] = y[13]; a.state[17 * N + e] = W3;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) a.integ[i * N + e] = In[i];
+                if (c.diagnostics) {
+                    // per-step sums -- attempt histogram, reward, benchmark reward, projections -- with diagnostics only
+                    // (kernel-uniform); the mean attempt count is always available from the nfev sum (2 + 12 per attempt),
+                    // returns from the episode statistics
+                    const int att = (nf - 2) / 12;
+                    const int s_proj = __reduce_add_sync(FULL, nproj);
+                    const unsigned m1 = __ballot_sync(FULL, finl && att == 1), m2 = __ballot_sync(FULL, finl && att == 2);
+                    const unsigned m3 = __ballot_sync(FULL, finl && att == 3), m4 = __ballot_sync(FULL, finl && att >= 4);
+                    const float s_rew = warp_sum_f(rew0f);
+                    float s_brew = 0.f;
+                    if (MODE != 0) {
+                        const float rb = -sqrtf(fmaf(bex2, bex2, fmaf(bex1, bex1, bex0 * bex0))) - fabsf(beb1 * 3.14159265358979f);
+                        s_brew = warp_sum_f(finl ? fminf(fmaxf(fmaf(rb, 0.5f, 1.0f), 0.f), 1.f) : 0.f);
                     }
-                    a.ep_return[e] = ep_ret0;
-                    if (G == 2) a.ep_return[N + e] = ep_ret1;
-                    a.ep_length[e] = ep_len;
-                    a.ep_index[e] = ep_idx;
-                    busy = false;
+                    if (lane == 0) {
+                        ws[15] += (double)s_proj;
+                        ws[10] += (double)__popc(m1); ws[11] += (double)__popc(m2); ws[12] += (double)__popc(m3); ws[13] += (double)__popc(m4);
+                        ws[14] += (double)s_rew; ws[16] += (double)s_brew;
+                    }
                 }
             }
+            __syncwarp();
         }
         // ---- A2: idle lanes adopt the env fetched in A0 ----
         if (has_next && !busy) {
@@ -664,7 +676,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             bool do_reset = false;
             int64_t r_e = 0; uint32_t r_ep = 0; float *r_o1 = nullptr, *r_o2 = nullptr;
             int r_k = 0;   // the sub-step that ended the episode
-            if (rq_n >= QR_RESET_BATCH || (drained && rq_n > 0)) {
+            if (rq_n >= QR_RESET_BATCH || (drained && rq_n > 0)) {   // (warp-uniform; at least one lane resets)
                 // at most 32 per pass; a burst (e.g. a common time limit) leaves the rest for the next round.  Neither queue can
                 // overflow: envs in flight (in a lane, in RQ or in CQ) only increase when a lane takes an env from the tile
                 // sequence, which it does only when CQ is empty, i.e. when they number at most 32 + QR_RESET_BATCH - 1.
@@ -674,12 +686,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     if (MULTI) r_k = rqk[rq_n - n_now + lane] - 1;
                     const bool r_last = r_k == NS - 1;
                     r_ep = __ldcg(a.ep_index + r_e);   // written when the env was released (already incremented)
-                    r_o1 = a.obs_roll ? a.obs_roll + ((int64_t)r_k * N + r_e) * O : ((r_last || POLICY) ? a.obs + r_e * OS : nullptr);
-                    r_o2 = (a.obs_roll && (r_last || POLICY)) ? a.obs + r_e * OS : nullptr;
+                    r_o1 = (MULTI && a.obs_roll) ? a.obs_roll + ((int64_t)r_k * N + r_e) * O : ((r_last || POLICY) ? a.obs + r_e * OS : nullptr);
+                    r_o2 = (MULTI && a.obs_roll && (r_last || POLICY)) ? a.obs + r_e * OS : nullptr;
                 }
                 rq_n -= n_now;
-            }
-            if (__any_sync(FULL, do_reset)) {
                 obs_in_tile = false;   // the reset scratch and the park area overwrite the tile
                 __syncwarp();
                 T* const pk = ks + 1024 + lane;   // park slot j of this lane: pk[j * 32] (the reset scratch is ks[0 .. 1023])
@@ -756,24 +766,22 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const bool staged_act = a.actions && (a.act_f32 || sizeof(T) == 8);   // what A0 can stage (kernel-uniform)
             const bool staged = MULTI ? fresh : true;   // adopted in this round's A2: action, parameters and b1d were fetched ahead into the stash
             fresh = false;
-            if (staged) cp_async_wait_group<1>();   // everything but A2's group (end-of-step values, not needed yet)
+            // everything but A2's group (end-of-step values, not needed yet).  (A lane that keeps its env must not wait here:
+            //  on its last sub-step the group it would wait for is the fetch-ahead of its NEXT env, issued a moment ago.)
+            if (MULTI) cp_async_wait_group_if<1>(staged); else cp_async_wait_group<1>();
             // the parameters stay in the landing zone of the stash for as long as the env stays in this lane (only a lane that is
             // idle or on its last sub-step is handed a next env, A0): later sub-steps read them from there, not from HBM
             p_m = sh[(S_PAR + 0) * 32]; p_J1 = sh[(S_PAR + 2) * 32]; p_J3 = sh[(S_PAR + 3) * 32]; p_ctw = sh[(S_PAR + 5) * 32];
             if (MODE == 0) { p_d = sh[(S_PAR + 1) * 32]; p_ctf = sh[(S_PAR + 4) * 32]; }
-            if (staged) {
-                if (staged_act) {
+            if (staged && staged_act) {
 #pragma unroll
-                    for (int i = 0; i < A; ++i)
-                        act[i] = a.act_f32 ? (T)*reinterpret_cast<const float*>(sh + (S_ACT + i) * 32) : sh[(S_ACT + i) * 32];
-                }
-                if (GOAL1) {
+                for (int i = 0; i < A; ++i)
+                    act[i] = a.act_f32 ? (T)*reinterpret_cast<const float*>(sh + (S_ACT + i) * 32) : sh[(S_ACT + i) * 32];
+            }
+            if (GOAL1) {   // fetched ahead -- or the b1d of the step before (constant within an episode in mode 0), kept for the observation
+                const T* const bp = sh + (staged ? S_NB1D : S_B1D) * 32;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) b1d[i] = sh[(S_NB1D + i) * 32];
-                }
-            } else if (GOAL1) {   // b1d of the step before (constant within an episode in mode 0), kept for the observation
-#pragma unroll
-                for (int i = 0; i < 3; ++i) b1d[i] = sh[(S_B1D + i) * 32];
+                for (int i = 0; i < 3; ++i) b1d[i] = bp[i * 32];
             }
             if (a.actions && !(staged && staged_act)) {
                 const int64_t base = ((int64_t)k * N + e) * A;
@@ -885,10 +893,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 traj_wd<T>(y + 3, Wv, b1d, Wd);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { sh[(S_B1D + i) * 32] = b1d[i]; sh[(S_WD + i) * 32] = Wd[i]; }   // for the observation at the end
-                if (k == NS - 1) {   // visible in the goal buffer like env.Wd after set_goal_state
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) a.goal[(9 + i) * N + e] = Wd[i];
-                }
+                for (int i = 0; i < 3; ++i) st_if(k == NS - 1, a.goal + (9 + i) * N + e, Wd[i]);   // visible in the goal buffer like env.Wd after set_goal_state
             }
             T f, M[3];
             action_to_fM<T>(r, c, act, act_f32, f, M, MODE);

@@ -113,9 +113,9 @@ int launch_step(qr_handle* h, int64_t lo, int64_t hi, const void* actions, int a
     if (grid > h->num_sms) grid = h->num_sms;
     if (ntiles < (int64_t)warps) warps = (int)ntiles;
     const size_t smem = per_warp * warps;
-    // single-step launches queue the envs whose episode ended and reset them in a second kernel; multi-step
-    // launches (the env keeps stepping in its lane) reset inside the step kernel
-    const bool multi = n_steps > 1 || policy;   // the policy variants exist for the in-kernel reset flavour only
+    // the multi-step kernel (the env keeps stepping in its lane) also serves every launch that writes the caller's rollout
+    // storage -- the single-step kernel has no code for it -- and the policy variants, which exist in that flavour only
+    const bool multi = n_steps > 1 || policy || obs_roll || reward_roll || done_roll;
     const bool goal1 = h->cfg.goal_mode == QR_GOAL_TRAJ_MODE0;   // only with a wrapper mode (checked in qr_create)
     // the kernel for this configuration (compiled in its own translation unit, qr_step_tu.cu)
     const qr::step_kernel_t<T> kern = qr::step_kernel<T>(h->cfg.mode, multi, goal1, policy && h->cfg.mode != QR_MODE_QUAD);

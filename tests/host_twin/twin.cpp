@@ -125,7 +125,7 @@ int step_one(const qr_config* cfg, const double* state, const double* integ, con
     } else {
         int f2 = norm_error_state<T>(r, c, o, MODE);
         if (f2 & 2) st |= 4;
-        reward_done<T>(c, o, rew, dn, MODE);
+        reward_done<T, double>(c, o, rew, dn, MODE);
     }
     for (int i = 0; i < 3; ++i) { state_out[i] = (double)x[i]; state_out[3 + i] = (double)y[i]; }
     for (int i = 0; i < 9; ++i) state_out[6 + i] = (double)y[3 + i];

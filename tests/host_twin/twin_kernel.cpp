@@ -54,7 +54,7 @@ struct tw_arrays {
 extern "C" int tw_kstep(const qr_config* cfg, const tw_arrays* b, int64_t env_lo, int64_t env_hi, int n_steps, int warps, int policy)
 {
     unsigned long long tile_counter[2] = {0, 0};
-    const bool multi = n_steps > 1 || policy, goal1 = cfg->goal_mode == QR_GOAL_TRAJ_MODE0;   // as launch_step()
+    const bool multi = n_steps > 1 || policy || b->obs_roll || b->reward_roll || b->done_roll, goal1 = cfg->goal_mode == QR_GOAL_TRAJ_MODE0;   // as launch_step()
     if (policy && cfg->mode == QR_MODE_QUAD) return -2;
     if (warps < 1 || warps > 12) return -1;
     blockDim.x = (unsigned)warps * 32; gridDim.x = 1; blockIdx.x = 0;

@@ -239,6 +239,31 @@ def test_kernel_rollout_with_autoreset_equals_single_steps(libs, dtype64, act64)
     assert e1.stats[0] == e2.stats[0] >= 2 * n and e1.stats[7] == e2.stats[7] == steps * n
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_kernel_one_step_rollout_with_storage_equals_step(libs, mode):
+    """qr_rollout(n_steps = 1) into the caller's arrays (served by the multi-step kernel: the single-step kernel carries no
+    code for rollout storage) against a plain step: rows, rewards, dones, every env array, with resets in both."""
+    K, F = libs
+    n = 131
+    kw = dict(n_envs=n, seed=8, autoreset=1, goal_mode=1, max_episode_steps=3, diagnostics=1)
+    c1, c2 = _config(mode, True, **kw), _config(mode, True, **kw)
+    e1, e2 = HostEnv(K, c1, warps=2), HostEnv(K, c2, warps=3)
+    _reset_all(F, c1, e1); _reset_all(F, c2, e2)
+    rng = np.random.default_rng(21)
+    for t in range(5):
+        act = rng.uniform(-1, 1, (n, e1.A))
+        obs_r, rew_r, done_r = e1.launch(act[None], n_steps=1, store=True)
+        e2.launch(act)
+        assert np.array_equal(e1.obs, e2.obs) and np.array_equal(e1.final_obs, e2.final_obs), t
+        assert np.array_equal(rew_r[0], e2.reward) and np.array_equal(done_r[0], e2.done)
+        # the stored row is the step's own observation; the handle's row of an env that was reset is its new episode's first
+        keep = ~(e2.terminated | e2.truncated).astype(bool)
+        assert np.array_equal(obs_r[0][keep], e2.obs[keep])
+        for name in ("state", "integ", "params", "goal", "reward", "done", "terminated", "truncated", "nfev", "ep_length", "ep_index", "ep_return"):
+            assert np.array_equal(getattr(e1, name), getattr(e2, name)), (name, t)
+    assert np.array_equal(e1.stats, e2.stats) and e1.stats[0] >= n
+
+
 def test_kernel_autoreset_equals_manual_protocol(libs):
     """The kernel's auto reset against step -> reset -> goal -> get_norm_error_state done env by env with the per-env
     functions (main.py:212-230): states, goals, parameters, first observations of the new episodes, final_obs."""

@@ -45,21 +45,25 @@ for l in dis[start + 1:]:
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out))); h = rows[1]
 iN, iX = h.index("# Samples"), h.index("Instructions Executed")
+STALLS = [c for c in os.environ.get("STALLS", "").split(",") if c]          # e.g. STALLS=stall_no_inst,stall_wait,stall_math
+iS = [h.index(c) for c in STALLS]
 data = []
 for r in rows[2:]:
     if r and r[0] == "Kernel Name": break
-    try: data.append((int(r[iN]), int(r[iX])))
+    try: data.append((int(r[iN]), int(r[iX])) + tuple(int(r[i] or 0) for i in iS))
     except Exception: pass
 assert len(seq) == len(data), (len(seq), len(data))
 ns, nx = sum(d[0] for d in data), sum(d[1] for d in data)
-agg = collections.defaultdict(lambda: [0, 0, 0])
-for g, (smp, x) in zip(seq, data):
+agg = collections.defaultdict(lambda: [0, 0, 0] + [0] * len(STALLS))
+for g, (smp, x, *st) in zip(seq, data):
     if not g: key = ("?", "?")
     else:
         outer = g[-1]
         callee = func_of(g[-2]) if len(g) >= 2 else "-"
         key = ("%s:%d" % outer if outer[0] == top_file else "%s:%d" % outer, callee)
     a = agg[key]; a[0] += 1; a[1] += x; a[2] += smp
-print("%-26s %-22s %6s %8s %8s" % ("call site", "inlined callee", "static", "dyn %", "samples %"))
-for (site, callee), (c, x, smp) in sorted(agg.items(), key=lambda kv: -kv[1][2])[: int(os.environ.get("TOP", "45"))]:
-    print("%-26s %-22s %6d %7.2f%% %7.2f%%" % (site, callee, c, 100.0 * x / nx, 100.0 * smp / ns))
+    for i, v in enumerate(st): a[3 + i] += v
+tot = [sum(a[3 + i] for a in agg.values()) or 1 for i in range(len(STALLS))]
+print("%-26s %-22s %6s %8s %8s" % ("call site", "inlined callee", "static", "dyn %", "samples %") + "".join(" %9s" % c.replace("stall_", "")[:9] for c in STALLS))
+for (site, callee), (c, x, smp, *st) in sorted(agg.items(), key=lambda kv: -kv[1][int(os.environ.get('SORT', '2'))])[: int(os.environ.get("TOP", "45"))]:
+    print("%-26s %-22s %6d %7.2f%% %7.2f%%" % (site, callee, c, 100.0 * x / nx, 100.0 * smp / ns) + "".join(" %8.2f%%" % (100.0 * v / t) for v, t in zip(st, tot)))
