@@ -128,12 +128,10 @@ QR_DEV void sts_if(bool p, double* s, double v)
 {
     asm volatile("{ .reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.f64 [%1], %2; }" ::"r"((int)p), "r"((unsigned)__cvta_generic_to_shared(s)), "d"(v) : "memory");
 }
-template <int N> QR_DEV void cp_async_wait_group_if(bool p) { asm volatile("{ .reg .pred q; setp.ne.s32 q, %0, 0; @q cp.async.wait_group %1; }" ::"r"((int)p), "n"(N) : "memory"); }
 #else
 QR_DEV void st_if(bool p, float* g, float v) { if (p) *g = v; }
 QR_DEV void st_if(bool p, double* g, double v) { if (p) *g = v; }
 QR_DEV void sts_if(bool p, double* s, double v) { if (p) *s = v; }
-template <int N> QR_DEV void cp_async_wait_group_if(bool) {}
 #endif
 template <typename T> QR_DEV int32_t& stash_i32(T* sh, int slot) { return *reinterpret_cast<int32_t*>(sh + slot * 32); }
 
@@ -768,36 +766,37 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             fresh = false;
             // everything but A2's group (end-of-step values, not needed yet).  (A lane that keeps its env must not wait here:
             //  on its last sub-step the group it would wait for is the fetch-ahead of its NEXT env, issued a moment ago.)
-            if (MULTI) cp_async_wait_group_if<1>(staged); else cp_async_wait_group<1>();
+            if (staged) cp_async_wait_group<1>();
             // the parameters stay in the landing zone of the stash for as long as the env stays in this lane (only a lane that is
             // idle or on its last sub-step is handed a next env, A0): later sub-steps read them from there, not from HBM
             p_m = sh[(S_PAR + 0) * 32]; p_J1 = sh[(S_PAR + 2) * 32]; p_J3 = sh[(S_PAR + 3) * 32]; p_ctw = sh[(S_PAR + 5) * 32];
             if (MODE == 0) { p_d = sh[(S_PAR + 1) * 32]; p_ctf = sh[(S_PAR + 4) * 32]; }
-            if (staged && staged_act) {
-#pragma unroll
-                for (int i = 0; i < A; ++i)
-                    act[i] = a.act_f32 ? (T)*reinterpret_cast<const float*>(sh + (S_ACT + i) * 32) : sh[(S_ACT + i) * 32];
-            }
             if (GOAL1) {   // fetched ahead -- or the b1d of the step before (constant within an episode in mode 0), kept for the observation
                 const T* const bp = sh + (staged ? S_NB1D : S_B1D) * 32;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) b1d[i] = bp[i * 32];
             }
-            if (a.actions && !(staged && staged_act)) {
-                const int64_t base = ((int64_t)k * N + e) * A;
-                if (a.act_f32) {
-                    const float* p = (const float*)a.actions + base;
-                    if (A == 4) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-                        act[0] = (T)v.x; act[1] = (T)v.y; act[2] = (T)v.z; act[3] = (T)v.w;
+            if (a.actions) {   // (one test on the path of in-kernel actions)
+                if (staged && staged_act) {
+#pragma unroll
+                    for (int i = 0; i < A; ++i)
+                        act[i] = a.act_f32 ? (T)*reinterpret_cast<const float*>(sh + (S_ACT + i) * 32) : sh[(S_ACT + i) * 32];
+                } else {
+                    const int64_t base = ((int64_t)k * N + e) * A;
+                    if (a.act_f32) {
+                        const float* p = (const float*)a.actions + base;
+                        if (A == 4) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+                            act[0] = (T)v.x; act[1] = (T)v.y; act[2] = (T)v.z; act[3] = (T)v.w;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
+                        }
                     } else {
+                        const double* p = (const double*)a.actions + base;
 #pragma unroll
                         for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                     }
-                } else {
-                    const double* p = (const double*)a.actions + base;
-#pragma unroll
-                    for (int i = 0; i < A; ++i) act[i] = (T)__ldg(p + i);
                 }
             }
             if (!GOAL1 && !(MODE != 0 && c.goal_mode >= 2)) {   // the observation at the end of this step reads the goal: have it in L2 by then
