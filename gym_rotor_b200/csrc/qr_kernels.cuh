@@ -280,15 +280,15 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     const int64_t ntiles = (n_range + 31) >> 5;
     // (dealing the tiles round robin instead -- no atomic, whose answer is the most stalled-on instruction of single-step
     //  launches -- measured 1.5 % to 3.7 % slower: profiles/r02/r02aa_ab_static_tiles.txt)
-    int64_t tile_base = 0;    // warp-uniform: first env of the tile currently being handed out
-    int tile_pos = 32;        // warp-uniform: envs of that tile already taken (32 = none left)
-    bool exhausted = false;   // warp-uniform: the counter ran past the last tile
+    // (env indices are 32-bit in the kernel: qr_create refuses more than 2^30 envs per handle -- 366 B each; three registers)
+    int tile_base = 0;        // warp-uniform: first env of the tile currently being handed out
+    int tile_pos = 32;        // warp-uniform: envs of that tile already taken (32 = none left, 33 = the counter ran past the last tile)
 
     // per-lane persistent state (registers).  Everything that is only needed when a step ENDS -- integral
     // errors, the goal of the step in flight, episode return / length / index -- lives in the lane's stash in
     // shared memory instead: 168 registers are all a thread gets at 12 warps per SM.
     bool busy = false, fin = false, need_init = false;
-    int64_t e = 0;
+    int e = 0;
     int k = 0;
     T x[3], y[14], W3 = 0, K0[14];
     Dyn<T> d;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
     bool fresh = false;      // the env was adopted in this round's A2: its action / parameters / b1d are in the stash
     bool r_ok = false;       // multi-step launches: the attitude passed ensure_SO3 in the observation that ended the previous sub-step
     bool obs_in_tile = false;   // policy rollouts: this round's A1 left the lane's observation row in the shared tile (stage storage)
-    int64_t e_next = 0;
+    int e_next = 0;
     int k_next = 0;          // multi-step launches: the sub-step at which the fetched env goes on (a reset env resumes mid-rollout)
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = 0;
@@ -325,29 +325,28 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const unsigned need = __ballot_sync(FULL, (!busy || leaving) && !has_next);
             const int cnt = __popc(need);
             const int ncq = MULTI ? min(cnt, cq_n) : 0;   // reset envs waiting to go on stepping are served first
-            if (cnt && (ncq > 0 || !(exhausted && tile_pos >= 32))) {
+            if (cnt && (ncq > 0 || tile_pos <= 32)) {
                 const bool mine = (need >> lane) & 1u;
                 const int rank = __popc(need & ((1u << lane) - 1u)) - ncq;   // < 0: this lane takes a waiting env
-                int64_t ee = a.env_hi;
+                int ee = 0x7fffffff;
                 int kk = 0;
-                if (MULTI && mine && rank < 0) { ee = (int64_t)cq[cq_n + rank]; kk = cqk[cq_n + rank]; }
+                if (MULTI && mine && rank < 0) { ee = cq[cq_n + rank]; kk = cqk[cq_n + rank]; }
                 cq_n -= ncq;
                 const int cnt_t = cnt - ncq;   // lanes served from the tile sequence
-                if (cnt_t > 0 && !(exhausted && tile_pos >= 32)) {
+                if (cnt_t > 0 && tile_pos <= 32) {
                     const int rem = 32 - tile_pos;
-                    int64_t base2 = -1;
-                    if (cnt_t > rem && !exhausted) {
+                    int base2 = -1;
+                    if (cnt_t > rem) {
                         unsigned long long t = 0;
                         if (lane == 0) t = atomicAdd(a.tile_counter, 1ULL);
                         t = __shfl_sync(FULL, t, 0);
-                        if ((int64_t)t < ntiles) base2 = a.env_lo + ((int64_t)t << 5);
-                        else exhausted = true;
+                        if ((int64_t)t < ntiles) base2 = (int)(a.env_lo + ((int64_t)t << 5));
                     }
                     if (mine && rank >= 0) {
                         if (rank < rem) ee = tile_base + tile_pos + rank;
                         else if (base2 >= 0) ee = base2 + (rank - rem);
                     }
-                    if (cnt_t > rem) { tile_base = base2; tile_pos = (base2 >= 0) ? cnt_t - rem : 32; }
+                    if (cnt_t > rem) { tile_base = base2; tile_pos = (base2 >= 0) ? cnt_t - rem : 33; }
                     else tile_pos += cnt_t;
                 }
                 if (ee < a.env_hi) {
@@ -405,7 +404,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
             const bool finl = fin;
             const bool last = (k == NS - 1);
             // all 32 lanes finish the same sub-step of 32 consecutive envs, first one 4-aligned (16-byte aligned rows block)
-            const int64_t e_first = __shfl_sync(FULL, e, 0);
+            const int e_first = __shfl_sync(FULL, e, 0);
             const int k_first = __shfl_sync(FULL, k, 0);
             const bool same = __all_sync(FULL, e - lane == e_first && k == k_first);   // (no warp primitive behind a short-circuit)
             // padded rows are 16-byte aligned; dense rollout rows: per lane.  (`same` makes `last` warp-uniform.)
@@ -484,8 +483,8 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         float *obs1 = nullptr, *obs2 = nullptr;   // where this step's observation row goes
                         if (MULTI && a.obs_roll) {   // kernel-uniform: caller's rollout storage (dense rows), plus the handle's row where it is read back
                             obs1 = a.obs_roll + ((int64_t)k * N + e) * O;
-                            if (last || POLICY) obs2 = a.obs + e * OS;   // POLICY: the actor reads a.obs at the next sub-step
-                        } else obs1 = a.obs + e * OS;
+                            if (last || POLICY) obs2 = a.obs + (int64_t)e * OS;   // POLICY: the actor reads a.obs at the next sub-step
+                        } else obs1 = a.obs + (int64_t)e * OS;
                         if (coop || (POLICY && MULTI)) {
                             // (policy rollouts: the actor of the next sub-step reads the row from here, not from HBM -- unless a
                             //  reset batch reuses the stage storage in between, see A3)
@@ -525,13 +524,13 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                         dd[0] = (uint8_t)dn[0]; if (G == 2) dd[1] = (uint8_t)dn[1];
                     }
                     if (last) {
-                        a.reward[e * G] = rew[0]; if (G == 2) a.reward[e * G + 1] = rew[1];
-                        a.done[e * G] = (uint8_t)dn[0]; if (G == 2) a.done[e * G + 1] = (uint8_t)dn[1];
+                        a.reward[(int64_t)e * G] = rew[0]; if (G == 2) a.reward[(int64_t)e * G + 1] = rew[1];
+                        a.done[(int64_t)e * G] = (uint8_t)dn[0]; if (G == 2) a.done[(int64_t)e * G + 1] = (uint8_t)dn[1];
                         a.terminated[e] = (uint8_t)term; a.truncated[e] = (uint8_t)trunc;
                         if (c.diagnostics) a.nfev[e] = nf;
                         if (epd) {
 #pragma unroll
-                            for (int i = 0; i < O; ++i) a.final_obs[e * OS + i] = o[i];
+                            for (int i = 0; i < O; ++i) a.final_obs[(int64_t)e * OS + i] = o[i];
                         }
                     }
                     if (st) a.status[e] |= (uint8_t)st;
@@ -587,7 +586,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     __syncwarp();
                     const float4* tile4 = reinterpret_cast<const float4*>(ks);
                     constexpr int NV = 32 * OS / 4;   // float4 elements of the 32-row block (rows padded)
-                    float4* g1 = reinterpret_cast<float4*>(a.obs + e_first * OS);
+                    float4* g1 = reinterpret_cast<float4*>(a.obs + (int64_t)e_first * OS);
 #pragma unroll
                     for (int it = 0; it < (NV + 31) / 32; ++it) {
                         const int q = it * 32 + lane;
@@ -600,7 +599,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     // reset at once.  RQ holds 64: at most QR_RESET_BATCH - 1 entries from earlier rounds + 32 new ones
                     if (ep_done) {
                         const int q = rq_n + __popc(mres & ((1u << lane) - 1u));
-                        rq[q] = (int32_t)e; if (MULTI) rqk[q] = (int16_t)k;   // the env goes on at the next sub-step (k: already advanced)
+                        rq[q] = e; if (MULTI) rqk[q] = (int16_t)k;   // the env goes on at the next sub-step (k: already advanced)
                     }
                     rq_n += __popc(mres);
                     const int s_len = __reduce_add_sync(FULL, ep_len_done);
@@ -672,7 +671,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
         // the env's own lane -- one lane working, 31 waiting, in 40 % of the rounds -- cost 14 % of the launch. ----
         {
             bool do_reset = false;
-            int64_t r_e = 0; uint32_t r_ep = 0; float *r_o1 = nullptr, *r_o2 = nullptr;
+            int r_e = 0; uint32_t r_ep = 0; float *r_o1 = nullptr, *r_o2 = nullptr;
             int r_k = 0;   // the sub-step that ended the episode
             if (rq_n >= QR_RESET_BATCH || (drained && rq_n > 0)) {   // (warp-uniform; at least one lane resets)
                 // at most 32 per pass; a burst (e.g. a common time limit) leaves the rest for the next round.  Neither queue can
@@ -680,12 +679,12 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 // sequence, which it does only when CQ is empty, i.e. when they number at most 32 + QR_RESET_BATCH - 1.
                 const int n_now = min(rq_n, 32);
                 if (lane < n_now) {
-                    do_reset = true; r_e = (int64_t)rq[rq_n - n_now + lane];
+                    do_reset = true; r_e = rq[rq_n - n_now + lane];
                     if (MULTI) r_k = rqk[rq_n - n_now + lane] - 1;
                     const bool r_last = r_k == NS - 1;
                     r_ep = __ldcg(a.ep_index + r_e);   // written when the env was released (already incremented)
-                    r_o1 = (MULTI && a.obs_roll) ? a.obs_roll + ((int64_t)r_k * N + r_e) * O : ((r_last || POLICY) ? a.obs + r_e * OS : nullptr);
-                    r_o2 = (MULTI && a.obs_roll && (r_last || POLICY)) ? a.obs + r_e * OS : nullptr;
+                    r_o1 = (MULTI && a.obs_roll) ? a.obs_roll + ((int64_t)r_k * N + r_e) * O : ((r_last || POLICY) ? a.obs + (int64_t)r_e * OS : nullptr);
+                    r_o2 = (MULTI && a.obs_roll && (r_last || POLICY)) ? a.obs + (int64_t)r_e * OS : nullptr;
                 }
                 rq_n -= n_now;
                 obs_in_tile = false;   // the reset scratch and the park area overwrite the tile
@@ -701,10 +700,10 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 pk[39 * 32] = ode.t; pk[40 * 32] = ode.h_abs;
                 QR_PKI(41) = ode.rejected; QR_PKI(42) = ode.nfev; QR_PKI(43) = ode.status; QR_PKI(44) = ode.nproj; QR_PKI(45) = ode.checked;
                 if (MULTI) QR_PKI(46) = k;
-                QR_PKI(47) = (int)busy | ((int)fin << 1) | ((int)need_init << 2) | ((int)has_next << 3) | ((int)exhausted << 4) | ((int)(MULTI && fresh) << 5) | ((int)(MULTI && r_ok) << 6);
-                QR_PKI(48) = (int32_t)(uint32_t)e; QR_PKI(49) = (int32_t)(e >> 32);
-                QR_PKI(50) = (int32_t)(uint32_t)e_next; QR_PKI(51) = (int32_t)(e_next >> 32);
-                QR_PKI(52) = (int32_t)(uint32_t)tile_base; QR_PKI(53) = (int32_t)(tile_base >> 32);
+                QR_PKI(47) = (int)busy | ((int)fin << 1) | ((int)need_init << 2) | ((int)has_next << 3) | ((int)(MULTI && fresh) << 5) | ((int)(MULTI && r_ok) << 6);
+                QR_PKI(48) = e;
+                QR_PKI(50) = e_next;
+                QR_PKI(52) = tile_base;
                 QR_PKI(54) = tile_pos; QR_PKI(55) = rq_n;
                 if (MULTI) { QR_PKI(56) = cq_n; QR_PKI(57) = k_next; }
                 if (do_reset) {
@@ -723,11 +722,11 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 if (MULTI) k = QR_PKI(46);
                 {
                     const int fl = QR_PKI(47);
-                    busy = fl & 1; fin = (fl >> 1) & 1; need_init = (fl >> 2) & 1; has_next = (fl >> 3) & 1; exhausted = (fl >> 4) & 1; fresh = (fl >> 5) & 1; r_ok = (fl >> 6) & 1;
+                    busy = fl & 1; fin = (fl >> 1) & 1; need_init = (fl >> 2) & 1; has_next = (fl >> 3) & 1; fresh = (fl >> 5) & 1; r_ok = (fl >> 6) & 1;
                 }
-                e = (int64_t)(((uint64_t)(uint32_t)QR_PKI(49) << 32) | (uint32_t)QR_PKI(48));
-                e_next = (int64_t)(((uint64_t)(uint32_t)QR_PKI(51) << 32) | (uint32_t)QR_PKI(50));
-                tile_base = (int64_t)(((uint64_t)(uint32_t)QR_PKI(53) << 32) | (uint32_t)QR_PKI(52));
+                e = QR_PKI(48);
+                e_next = QR_PKI(50);
+                tile_base = QR_PKI(52);
                 tile_pos = QR_PKI(54); rq_n = QR_PKI(55);
                 if (MULTI) { cq_n = QR_PKI(56); k_next = QR_PKI(57); }
 #undef QR_PKI
@@ -743,7 +742,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     const unsigned cm = __ballot_sync(FULL, cont);
                     if (cont) {
                         const int q = cq_n + __popc(cm & ((1u << lane) - 1u));
-                        cq[q] = (int32_t)r_e; cqk[q] = (int16_t)(r_k + 1);
+                        cq[q] = r_e; cqk[q] = (int16_t)(r_k + 1);
                     }
                     cq_n += __popc(cm);
                 }
@@ -813,7 +812,7 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                     for (int i = 0; i < OS / 4; ++i) { const float4 v = row[i]; xo[4 * i] = v.x; xo[4 * i + 1] = v.y; xo[4 * i + 2] = v.z; xo[4 * i + 3] = v.w; }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < O; ++i) xo[i] = a.obs[e * OS + i];
+                    for (int i = 0; i < O; ++i) xo[i] = a.obs[(int64_t)e * OS + i];
                 }
                 obs_in_tile = false;
                 if (MODE == 1) actor_td3_mono(xo, af);

@@ -174,7 +174,8 @@ int qr_create(const qr_config* c, int device, qr_handle** out)
     if (c->n_envs <= 0) return fail(QR_ERR_INVALID, "qr_create: n_envs must be positive");
     if (c->mode < 0 || c->mode > 2) return fail(QR_ERR_INVALID, "qr_create: bad mode");
     if (c->dtype != QR_F32 && c->dtype != QR_F64) return fail(QR_ERR_INVALID, "qr_create: bad dtype");
-    if (c->n_envs >= ((int64_t)1 << 31)) return fail(QR_ERR_INVALID, "qr_create: n_envs must be below 2^31 per handle");
+    // (the step kernel keeps env indices in 32-bit registers; 2^30 envs are 393 GB of env state in float32 mode anyway)
+    if (c->n_envs > ((int64_t)1 << 30)) return fail(QR_ERR_INVALID, "qr_create: n_envs must not exceed 2^30 per handle");
     if (c->integrator == QR_INT_EULER && c->mode != QR_MODE_QUAD)
         return fail(QR_ERR_INVALID, "qr_create: the Euler integrator exists only for the base Quad-v0 env (quad.py:252)");
     if (c->goal_mode < QR_GOAL_EXTERNAL || c->goal_mode > QR_GOAL_TRAJ_STAY) return fail(QR_ERR_INVALID, "qr_create: bad goal_mode");

@@ -65,7 +65,7 @@ typedef struct qr_handle qr_handle;
 /* Everything the reference reads from argparse defaults and constructor constants (args_parse.py:14-35,
  * quad.py:28-41,60-61,75-91,104-107, coupled:21-24), plus what is new for a batched device env. */
 typedef struct qr_config {
-    int64_t n_envs;             /* envs owned by this handle (this GPU's shard) */
+    int64_t n_envs;             /* envs owned by this handle (this GPU's shard), 1 .. 2^30 */
     int64_t env_id_offset;      /* global id of local env 0: Philox streams do not depend on the sharding */
     uint64_t seed;
     int32_t mode;               /* QR_MODE_* */
