@@ -576,10 +576,11 @@ __global__ void __launch_bounds__(step_threads<T>::value, 1) k_step(const __grid
                 const unsigned mbad = __ballot_sync(FULL, finl && st != 0);
                 const unsigned msolved = (MODE != 0) ? __ballot_sync(FULL, solved) : 0u;
                 const bool l0 = lane == 0;
-                sts_if(l0, ws + 7, ws[7] + (double)__popc(finmask));
-                sts_if(l0, ws + 9, ws[9] + (double)s_nfev);
-                sts_if(l0, ws + 8, ws[8] + (double)__popc(mbad));
-                if (MODE != 0) sts_if(l0, ws + 17, ws[17] + (double)__popc(msolved));
+                const double v7 = ws[7] + (double)__popc(finmask), v9 = ws[9] + (double)s_nfev, v8 = ws[8] + (double)__popc(mbad);
+                const double v17 = (MODE != 0) ? ws[17] + (double)__popc(msolved) : 0.0;
+                __syncwarp();   // every lane has read; lane 0 writes (the next reads are a round away, behind the barrier that ends A1)
+                sts_if(l0, ws + 7, v7); sts_if(l0, ws + 9, v9); sts_if(l0, ws + 8, v8);
+                if (MODE != 0) sts_if(l0, ws + 17, v17);
             }
             if (coop || mres != 0 || c.diagnostics) {   // (warp-uniform)
                 if (coop) {
