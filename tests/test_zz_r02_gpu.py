@@ -239,3 +239,39 @@ def test_fp32_mode_at_extreme_angular_rates(scale):
     assert int((d64 != d32).sum()) <= 2
     assert e64.stats()[15] > 1000 and e32.stats()[15] > 1000       # re-projections happened in both modes
     e64.close(); e32.close()
+
+
+@pytest.mark.parametrize("fw,dtype", [("MONO", torch.float32), ("MODUL", torch.float64)])
+def test_one_step_rollout_with_storage_equals_step(fw, dtype):
+    """qr_rollout(n_steps = 1) into the caller's arrays is served by the multi-step kernel (the single-step kernel carries no
+    code for rollout storage): rows, rewards, dones and every env array against a plain step, resets in both."""
+    n = 4099
+    kw = dict(autoreset=True, goal_mode="traj0", max_episode_steps=3, seed=8)
+    e1, e2 = _env(n, fw, dtype, **kw), _env(n, fw, dtype, **kw)
+    _start(e1); _start(e2)
+    rng = np.random.default_rng(21)
+    for t in range(5):
+        act = _t(rng.uniform(-1, 1, (n, e1.act_dim)), dtype)
+        obs_r, rew_r, done_r = e1.rollout(1, act[None].contiguous(), store=True)
+        obs, rew, done, _, _ = e2.step(act)
+        assert torch.equal(e1.obs, e2.obs) and torch.equal(e1.final_obs, e2.final_obs), t
+        assert torch.equal(rew_r[0], rew) and torch.equal(done_r[0].bool(), done)
+        keep = ~(e2.terminated.bool() | e2.truncated.bool())
+        assert torch.equal(obs_r[0][keep], torch.cat(obs, dim=1)[keep])
+        assert torch.equal(e1.state_soa, e2.state_soa) and torch.equal(e1.integ_soa, e2.integ_soa)
+    s1, s2 = e1.stats(), e2.stats()
+    assert np.array_equal(s1, s2) and s1[0] >= n
+    e1.close(); e2.close()
+
+
+def test_create_refuses_more_envs_than_the_kernel_indexes():
+    """Env indices are 32-bit inside the step kernel: qr_create caps a handle at 2^30 envs (before it allocates anything)."""
+    from gym_rotor_b200 import _native as nat
+    L = nat.load()
+    cfg = nat.QrConfig()
+    nat.check(L.qr_default_config(C.byref(cfg), 1, nat.F32))
+    cfg.n_envs = (1 << 30) + 1
+    h = C.c_void_p()
+    rc = L.qr_create(C.byref(cfg), 0, C.byref(h))
+    assert rc != 0 and not h.value
+    assert b"2^30" in L.qr_last_error()
