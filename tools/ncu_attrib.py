@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Attribute an ncu source-page capture of one kernel to (call-site line in the kernel, inlined callee) using
-nvdisasm -gi inline chains.  usage: ncu_attrib.py <rep> <lib.so> <mangled kernel substring> [kernel source file]"""
+nvdisasm -gi inline chains.  usage: ncu_attrib.py <rep> <lib.so> <mangled kernel substring> [kernel source file]
+env: TOP=<rows>, STALLS=stall_no_inst,stall_wait,... (adds each site's share of those stall samples; column names of
+`ncu --page source --csv`), SORT=<column index: 1 dynamic instructions, 2 samples, 3.. the STALLS columns>"""
 import bisect, collections, csv, io, os, re, subprocess, sys, tempfile
 
 rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
