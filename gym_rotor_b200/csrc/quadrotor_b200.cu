@@ -385,7 +385,8 @@ int qr_step_host(qr_handle* h, const void* actions_host, int act_dtype, float* o
     for (auto st : h->io_stream) QR_CUDA(cudaStreamWaitEvent(st, h->io_event[0], 0));
     // Chunked pipeline over the handle's two streams: copy-in, step and copy-out of chunk i overlap those of chunk i+1
     // through the copy engines; chunk boundaries are multiples of the block size so rows stay line aligned.
-    const int64_t target_chunks = 8;
+    // (QR_HOST_CHUNKS: measurement override, tools/e2e_chunks.sh)
+    static const int64_t target_chunks = [] { const char* e = getenv("QR_HOST_CHUNKS"); const long v = e ? atol(e) : 0; return (int64_t)(v >= 1 && v <= 256 ? v : 8); }();
     int64_t chunk = ((n + target_chunks - 1) / target_chunks + qr::QR_BLOCK - 1) / qr::QR_BLOCK * qr::QR_BLOCK;
     if (chunk < 16384) chunk = 16384;
     int idx = 0;
