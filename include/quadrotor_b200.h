@@ -163,7 +163,8 @@ int qr_rollout(qr_handle* h, int n_steps, const void* actions, int act_dtype, fl
  * obs (dense [N][obs_dim]) / reward / done device->host and returns when they are valid.  This is the call the
  * end-to-end benchmark times.  Any output pointer may be NULL.  The work is pipelined in chunks over two streams
  * owned by the handle; it is ordered after everything enqueued on `stream` so far (pass the stream of the caller's
- * earlier qr_* calls; NULL = the legacy default stream). */
+ * earlier qr_* calls; NULL = the legacy default stream).  (Eight chunks; the environment variable QR_HOST_CHUNKS, read
+ * once, overrides the count for measurements: throughput is flat from 4 to 16, profiles/r02/r02be_e2e_chunks.txt.) */
 int qr_step_host(qr_handle* h, const void* actions_host, int act_dtype, float* obs_host, void* reward_host,
                  uint8_t* done_host, void* stream);
 
